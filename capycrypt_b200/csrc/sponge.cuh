@@ -1,0 +1,251 @@
+// sponge.cuh -- batched sponge absorb/squeeze with the reference's exact byte layout.
+//
+// One thread owns one item.  The bytes an item absorbs are never materialised: they are a
+// *virtual stream*  P | KB | X | T | pad  that reproduces what the reference builds in a Vec
+// before absorbing:
+//   P   constant prefix  bytepad(encode_string(N) || encode_string(S), w)   cshake  shake_functions.rs:50-55
+//   KB  per-item key block bytepad(encode_string(K), w)                      kmac    shake_functions.rs:80-82
+//   X   the message
+//   T   trailer: 06|86 (SHA3-d, :25-29, quirk Q2) / 04 (cSHAKE :57) / 00 01 04 (KMACXOF :86 + :57)
+//   pad zeros then 0x80, ONLY when the length so far is not a multiple of the rate  sponge.rs:13-15,89-95 (Q1)
+// Blocks that lie wholly inside X are loaded straight from global memory (8-byte lanes,
+// little-endian = lane value); blocks touching a segment boundary are assembled per lane.
+// Absorb = sponge.rs:47-60 (bytes_to_state), squeeze = sponge.rs:25-34 without the wasted
+// trailing permutation (quirk Q8).
+#pragma once
+#include "keccak.cuh"
+
+namespace capy {
+
+struct SpongeJob {
+  // constant prefix segment
+  const uint8_t* prefix;
+  uint32_t prefix_len;
+  // state after the first skip_blocks blocks (all inside P) were absorbed; nullptr = zero state
+  const uint64_t* init_state;
+  uint32_t skip_blocks;
+  // per-item keys (nullptr = no key block).  key_off == nullptr -> fixed key_len at key_stride
+  const uint8_t* keys;
+  const uint64_t* key_off;
+  uint64_t key_stride;
+  uint32_t key_len;
+  uint32_t w;  // bytepad width (SecParam::bytepad_value, lib.rs:137-144)
+  // per-item messages.  off == nullptr -> fixed msg_len at msg_stride
+  const uint8_t* data;
+  const uint64_t* off;
+  uint64_t msg_stride;
+  uint64_t msg_len;
+  // trailer bytes, little-endian packed, trailer_len <= 4.  sha3_suffix: trailer is 0x86 when
+  // len % 136 == 135 else 0x06 (rate 136 hard-coded for every d, quirk Q2)
+  uint32_t trailer;
+  uint32_t trailer_len;
+  uint32_t sha3_suffix;
+  // fips_pad: FIPS 202 pad10*1 (0x80 is ORed into the last byte even when already aligned);
+  // only used by the SHAKE extras that have no reference counterpart
+  uint32_t fips_pad;
+  // q4_rate != 0: reference quirk Q4 (cshake with N = S = ""): after the 0x04 trailer the buffer
+  // was run through shake(): a 06|86 suffix chosen from (len % 136) and a first pad to q4_rate
+  uint32_t q4_rate;
+  // rate in bytes as the reference computes it ((1600 - c) / 8; 172 for D224 cSHAKE, quirk Q7)
+  uint32_t rate;
+  // output: out_off == nullptr -> out_bytes per item at out_stride
+  uint8_t* out;
+  const uint64_t* out_off;
+  uint64_t out_stride;
+  uint64_t out_bytes;
+  uint32_t sq_lanes;  // lanes emitted per squeeze block = (1600 - d) / 64
+  uint64_t n;
+  // optional permutation of work: item index = order ? order[t] : t (length-sorted launch)
+  const uint32_t* order;
+};
+
+__device__ __forceinline__ uint32_t left_encode_nbytes(uint64_t v) {
+  uint32_t nb = 1;
+  while (nb < 8 && (v >> (8 * nb)) != 0) nb++;
+  return nb;
+}
+
+// byte p of bytepad(encode_string(K), w) before zero padding (aux_functions.rs:11-49)
+__device__ __forceinline__ uint32_t key_block_byte(uint64_t p, const uint8_t* key, uint64_t klen, uint32_t w,
+                                                   uint32_t w_nb, uint32_t k_nb) {
+  // left_encode(w)
+  if (p == 0) return w_nb;
+  if (p <= w_nb) return (w >> (8 * (w_nb - p))) & 0xFF;
+  p -= 1 + w_nb;
+  // left_encode(8 * klen)
+  uint64_t bits = klen * 8;
+  if (p == 0) return k_nb;
+  if (p <= k_nb) return (uint32_t)(bits >> (8 * (k_nb - p))) & 0xFF;
+  p -= 1 + k_nb;
+  if (p < klen) return key[p];
+  return 0;
+}
+
+template <int LANES>
+__device__ __forceinline__ void sponge_item(const SpongeJob& J, uint64_t i) {
+  // ---- per-item stream geometry -----------------------------------------------------
+  const uint8_t* key = nullptr;
+  uint64_t klen = 0, kb_len = 0;
+  uint32_t w_nb = 1, k_nb = 1;
+  if (J.keys) {
+    if (J.key_off) {
+      key = J.keys + J.key_off[i];
+      klen = J.key_off[i + 1] - J.key_off[i];
+    } else {
+      key = J.keys + i * J.key_stride;
+      klen = J.key_len;
+    }
+    w_nb = left_encode_nbytes(J.w);
+    k_nb = left_encode_nbytes(klen * 8);
+    uint64_t content = (uint64_t)(1 + w_nb) + (1 + k_nb) + klen;
+    kb_len = (content / J.w + 1) * J.w;  // byte_pad always appends w - len % w zeros (quirk Q3)
+  }
+  const uint8_t* x;
+  uint64_t xlen;
+  if (J.off) {
+    x = J.data + J.off[i];
+    xlen = J.off[i + 1] - J.off[i];
+  } else {
+    x = J.data + i * J.msg_stride;
+    xlen = J.msg_len;
+  }
+  uint32_t trailer = J.trailer;
+  if (J.sha3_suffix) trailer = (xlen % 136u == 135u) ? 0x86u : 0x06u;
+  const uint64_t x0 = (uint64_t)J.prefix_len + kb_len;
+  const uint64_t x1 = x0 + xlen;
+  uint32_t trailer_len = J.trailer_len;
+  if (J.q4_rate) {  // shake_functions.rs:59-61 -> :25-29 on the buffer P|X|04
+    trailer |= (((x1 + 1) % 136u == 135u) ? 0x86u : 0x06u) << 8;
+    trailer_len = 2;
+  }
+  const uint64_t t1 = x1 + trailer_len;
+  // first pad (Q4 only): to a multiple of the SHA3-d rate, only when unaligned
+  uint64_t p1 = t1;
+  bool has_pad1 = false;
+  if (J.q4_rate) {
+    const uint64_t rem1 = t1 % J.q4_rate;
+    has_pad1 = rem1 != 0;
+    if (has_pad1) p1 = t1 + (J.q4_rate - rem1);
+  }
+  const uint64_t rem = p1 % J.rate;
+  const uint64_t padded = rem ? p1 + (J.rate - rem) : p1;  // Q1: no pad block when aligned
+  const uint64_t nblocks = padded / J.rate;
+  const bool has_pad = rem != 0;
+  if (J.fips_pad && !has_pad) trailer |= 0x80u << (8 * (trailer_len - 1));
+
+  Lane a[25];
+  if (J.init_state) {
+#pragma unroll
+    for (int k = 0; k < 25; k++) {
+      uint64_t v = J.init_state[k];
+      a[k].lo = (uint32_t)v;
+      a[k].hi = (uint32_t)(v >> 32);
+    }
+  } else {
+    state_zero(a);
+  }
+
+  // ---- absorb (sponge.rs:47-60) -------------------------------------------------------
+  constexpr uint64_t STRIDE = 8ull * LANES;  // bytes consumed per block (168 for the 172 quirk)
+  for (uint64_t b = J.skip_blocks; b < nblocks; b++) {
+    const uint64_t s = b * STRIDE;
+    if (s >= x0 && s + STRIDE <= x1) {
+      const uint8_t* p = x + (s - x0);
+      if ((reinterpret_cast<uintptr_t>(p) & 7u) == 0) {
+        const uint2* q = reinterpret_cast<const uint2*>(p);
+#pragma unroll
+        for (int j = 0; j < LANES; j++) {
+          uint2 v = __ldg(q + j);
+          a[j].lo ^= v.x;
+          a[j].hi ^= v.y;
+        }
+      } else {
+        // unaligned message start: aligned 32-bit words + funnel shift by the byte phase
+        const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 3u) * 8u;
+        const uint32_t* q = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)3);
+        uint32_t w0 = __ldg(q);
+#pragma unroll
+        for (int j = 0; j < LANES; j++) {
+          uint32_t w1 = __ldg(q + 2 * j + 1);
+          // the third word is only needed (and only guaranteed readable) when sh != 0
+          uint32_t w2 = (sh != 0 || j + 1 < LANES) ? __ldg(q + 2 * j + 2) : 0u;
+          a[j].lo ^= __funnelshift_r(w0, w1, sh);
+          a[j].hi ^= __funnelshift_r(w1, w2, sh);
+          w0 = w2;
+        }
+      }
+    } else {
+      // boundary block: assemble lane by lane from the virtual stream
+      uint64_t blk[LANES];
+#pragma unroll 1
+      for (int j = 0; j < LANES; j++) {
+        const uint64_t o = s + 8ull * j;
+        uint64_t v = 0;
+        if (o >= x0 && o + 8 <= x1) {
+          const uint8_t* p = x + (o - x0);
+#pragma unroll
+          for (int k = 0; k < 8; k++) v |= (uint64_t)p[k] << (8 * k);
+        } else {
+#pragma unroll 1
+          for (int k = 0; k < 8; k++) {
+            const uint64_t pos = o + k;
+            uint32_t byte;
+            if (pos < J.prefix_len) byte = J.prefix[pos];
+            else if (pos < x0) byte = key_block_byte(pos - J.prefix_len, key, klen, J.w, w_nb, k_nb);
+            else if (pos < x1) byte = x[pos - x0];
+            else if (pos < t1) byte = (trailer >> (8 * (uint32_t)(pos - x1))) & 0xFF;
+            else if (has_pad && pos == padded - 1) byte = 0x80;
+            else if (has_pad1 && pos == p1 - 1) byte = 0x80;
+            else byte = 0;
+            v |= (uint64_t)byte << (8 * k);
+          }
+        }
+        blk[j] = v;
+      }
+#pragma unroll
+      for (int j = 0; j < LANES; j++) {
+        a[j].lo ^= (uint32_t)blk[j];
+        a[j].hi ^= (uint32_t)(blk[j] >> 32);
+      }
+    }
+    keccak_f1600(a);
+  }
+
+  // ---- squeeze (sponge.rs:25-34, minus the dropped final permutation) -----------------------
+  uint8_t* o;
+  uint64_t out_bytes;
+  if (J.out_off) {
+    o = J.out + J.out_off[i];
+    out_bytes = J.out_off[i + 1] - J.out_off[i];
+  } else {
+    o = J.out + i * J.out_stride;
+    out_bytes = J.out_bytes;
+  }
+  const uint64_t sq_bytes = 8ull * J.sq_lanes;
+  const bool o_aligned = (reinterpret_cast<uintptr_t>(o) & 7u) == 0;
+  for (uint64_t produced = 0; produced < out_bytes;) {
+#pragma unroll
+    for (int j = 0; j < 21; j++) {
+      const uint64_t pos = produced + 8ull * j;
+      if (j < (int)J.sq_lanes && pos < out_bytes) {
+        if (o_aligned && pos + 8 <= out_bytes) {
+          *reinterpret_cast<uint2*>(o + pos) = make_uint2(a[j].lo, a[j].hi);
+        } else {
+          const uint64_t v = ((uint64_t)a[j].hi << 32) | a[j].lo;
+          for (int k = 0; k < 8 && pos + k < out_bytes; k++) o[pos + k] = (uint8_t)(v >> (8 * k));
+        }
+      }
+    }
+    produced += sq_bytes;
+    if (produced < out_bytes) keccak_f1600(a);
+  }
+}
+
+template <int LANES>
+__global__ void __launch_bounds__(128) sponge_kernel(const SpongeJob J) {
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= J.n) return;
+  sponge_item<LANES>(J, J.order ? (uint64_t)J.order[t] : t);
+}
+
+}  // namespace capy

@@ -1,0 +1,275 @@
+"""Array-level Python front end of the C ABI (host numpy buffers and device torch tensors).
+
+This is harness/plumbing: every function forwards to one C entry point of
+libcapycrypt_gpu.so (include/capy_gpu.h).  torch is used only for device memory and streams.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _binding as B
+
+
+def _u8(a) -> np.ndarray:
+    if isinstance(a, np.ndarray):
+        return np.ascontiguousarray(a, dtype=np.uint8).reshape(-1)
+    b = bytes(a)
+    return np.frombuffer(b, dtype=np.uint8).copy() if b else np.zeros(0, np.uint8)
+
+
+def _u64(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.uint64).reshape(-1)
+
+
+def _hp(a: np.ndarray | None):
+    """host address of a numpy buffer (a 1-byte dummy for empty arrays so it is never NULL)."""
+    if a is None:
+        return None
+    if a.size == 0:
+        return _DUMMY.ctypes.data
+    return a.ctypes.data
+
+
+_DUMMY = np.zeros(16, np.uint8)
+
+
+def pack(items) -> tuple[np.ndarray, np.ndarray]:
+    """list of bytes-like -> (packed u8, u64 offsets[n+1])."""
+    off = np.zeros(len(items) + 1, dtype=np.uint64)
+    if len(items):
+        off[1:] = np.cumsum([len(x) for x in items], dtype=np.uint64)
+    blob = b"".join(bytes(x) for x in items)
+    data = np.frombuffer(blob, dtype=np.uint8).copy() if blob else np.zeros(0, np.uint8)
+    return data, off
+
+
+class Engine:
+    """One capy_ctx.  devices=None -> current CUDA device."""
+
+    def __init__(self, devices=None):
+        self.lib = B.load()
+        self._ctx = C.c_void_p()
+        self._pinned = []
+        if devices is None:
+            rc = self.lib.capy_gpu_init(None, 0, C.byref(self._ctx))
+        else:
+            arr = (C.c_int * len(devices))(*devices)
+            rc = self.lib.capy_gpu_init(arr, len(devices), C.byref(self._ctx))
+        if rc != B.OK:
+            self._ctx = C.c_void_p()
+            raise B.CapyError(rc, self.lib.capy_strerror(rc).decode())
+
+    def close(self):
+        if getattr(self, "_ctx", None) and self._ctx.value:
+            for p in self._pinned:
+                self.lib.capy_host_free(p)
+            self._pinned = []
+            self.lib.capy_gpu_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- plumbing ----
+    def _check(self, rc: int, allow=()):
+        if rc != B.OK and rc not in allow:
+            msg = self.lib.capy_strerror(rc).decode()
+            if rc == B.ERR_CUDA:
+                msg += " -- " + self.lib.capy_last_cuda_error(self._ctx).decode()
+            raise B.CapyError(rc, msg)
+        return rc
+
+    @property
+    def device_count(self) -> int:
+        return self.lib.capy_gpu_device_count(self._ctx)
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.capy_launch_count(self._ctx))
+
+    def pinned(self, nbytes: int) -> np.ndarray:
+        """uint8 numpy view of pinned host memory (capy_host_alloc); freed by close()."""
+        p = self.lib.capy_host_alloc(max(nbytes, 1))
+        if not p:
+            raise MemoryError("capy_host_alloc failed")
+        self._pinned.append(p)
+        return np.ctypeslib.as_array((C.c_uint8 * max(nbytes, 1)).from_address(p))[:nbytes]
+
+    # =================================================================================
+    # host-buffer API (blocking)
+    # =================================================================================
+    def sha3(self, data, off, d: int) -> np.ndarray:
+        data, off = _u8(data), _u64(off)
+        n = len(off) - 1
+        out = np.zeros((n, max(d // 8, 0) if d in (224, 256, 384, 512) else 1), dtype=np.uint8)
+        self._check(self.lib.capy_sha3_batch(self._ctx, d, _hp(data), _hp(off), n, _hp(out), 0))
+        return out
+
+    def sha3_fixed(self, data, msg_len: int, stride: int, n: int, d: int, out: np.ndarray | None = None) -> np.ndarray:
+        data = _u8(data)
+        if out is None:
+            out = np.zeros((n, d // 8 if d in (224, 256, 384, 512) else 1), dtype=np.uint8)
+        self._check(self.lib.capy_sha3_batch_fixed(self._ctx, d, _hp(data), msg_len, stride, n, _hp(out), 0))
+        return out
+
+    def cshake(self, data, off, out_bits: int, fn: bytes, custom: bytes, d: int) -> np.ndarray:
+        data, off = _u8(data), _u64(off)
+        n = len(off) - 1
+        out = np.zeros((n, out_bits // 8), dtype=np.uint8)
+        fn_a, cs_a = _u8(fn), _u8(custom)
+        self._check(self.lib.capy_cshake_batch(self._ctx, d, _hp(data), _hp(off), n, _hp(fn_a), len(fn_a), _hp(cs_a),
+                                               len(cs_a), out_bits, _hp(out)))
+        return out
+
+    def kmac_xof(self, keys, key_off, data, off, out_bits: int, custom: bytes, d: int, out_off=None) -> np.ndarray:
+        keys, key_off, data, off = _u8(keys), _u64(key_off), _u8(data), _u64(off)
+        n = len(off) - 1
+        cs_a = _u8(custom)
+        if out_off is None:
+            out = np.zeros((n, out_bits // 8), dtype=np.uint8)
+            oo = None
+        else:
+            out_off = _u64(out_off)
+            out = np.zeros(int(out_off[-1]), dtype=np.uint8)
+            oo = _hp(out_off)
+        self._check(self.lib.capy_kmac_xof_batch(self._ctx, d, _hp(keys), _hp(key_off), _hp(data), _hp(off), n,
+                                                 _hp(cs_a), len(cs_a), out_bits, oo, _hp(out)))
+        return out
+
+    def ed448_fixed_base(self, scalars_be56) -> np.ndarray:
+        sc = _u8(scalars_be56)
+        n = len(sc) // 56
+        out = np.zeros((n, 112), dtype=np.uint8)
+        self._check(self.lib.capy_ed448_fixed_base_batch(self._ctx, _hp(sc), n, _hp(out)))
+        return out
+
+    def ed448_var_base(self, scalars_be56, points_xy112) -> tuple[int, np.ndarray]:
+        sc, pts = _u8(scalars_be56), _u8(points_xy112)
+        n = len(sc) // 56
+        out = np.zeros((n, 112), dtype=np.uint8)
+        rc = self._check(self.lib.capy_ed448_var_base_batch(self._ctx, _hp(sc), _hp(pts), n, _hp(out)),
+                         allow=(B.ERR_BAD_POINT,))
+        return rc, out
+
+    def ed448_keygen(self, pws, pw_off, d: int) -> np.ndarray:
+        pws, pw_off = _u8(pws), _u64(pw_off)
+        n = len(pw_off) - 1
+        out = np.zeros((n, 112), dtype=np.uint8)
+        self._check(self.lib.capy_ed448_keygen_batch(self._ctx, d, _hp(pws), _hp(pw_off), n, _hp(out)))
+        return out
+
+    def ed448_sign(self, pws, pw_off, msgs, msg_off, d: int) -> tuple[np.ndarray, np.ndarray]:
+        pws, pw_off, msgs, msg_off = _u8(pws), _u64(pw_off), _u8(msgs), _u64(msg_off)
+        n = len(pw_off) - 1
+        h = np.zeros((n, 56), dtype=np.uint8)
+        z = np.zeros((n, 56), dtype=np.uint8)
+        self._check(self.lib.capy_ed448_sign_batch(self._ctx, d, _hp(pws), _hp(pw_off), _hp(msgs), _hp(msg_off), n,
+                                                   _hp(h), _hp(z)))
+        return h, z
+
+    def ed448_verify(self, pub_xy112, msgs, msg_off, h56, z_be56, d: int) -> tuple[int, np.ndarray]:
+        pub, msgs, msg_off, h, z = _u8(pub_xy112), _u8(msgs), _u64(msg_off), _u8(h56), _u8(z_be56)
+        n = len(msg_off) - 1
+        ok = np.zeros(n, dtype=np.uint8)
+        rc = self._check(self.lib.capy_ed448_verify_batch(self._ctx, d, _hp(pub), _hp(msgs), _hp(msg_off), _hp(h),
+                                                          _hp(z), n, _hp(ok)), allow=(B.ERR_BAD_POINT,))
+        return rc, ok
+
+    def ed448_ecdh(self, k_rand56, pub_xy112, want_z: bool = True):
+        k, pub = _u8(k_rand56), _u8(pub_xy112)
+        n = len(k) // 56
+        wx = np.zeros((n, 56), dtype=np.uint8)
+        z = np.zeros((n, 112), dtype=np.uint8) if want_z else None
+        rc = self._check(self.lib.capy_ed448_ecdh_batch(self._ctx, _hp(k), _hp(pub), n, _hp(wx), _hp(z)),
+                         allow=(B.ERR_BAD_POINT,))
+        return rc, wx, z
+
+    # =================================================================================
+    # device-pointer API (async on torch's current stream); tensors are torch.uint8 / int64 CUDA
+    # =================================================================================
+    @staticmethod
+    def _stream():
+        import torch
+
+        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def sha3_dev(self, t_data, t_off, d: int, t_out, dev_index: int = 0):
+        n = t_off.numel() - 1
+        self._check(self.lib.capy_sha3_batch_dev(self._ctx, dev_index, self._stream(), d, t_data.data_ptr(),
+                                                 t_off.data_ptr(), n, t_out.data_ptr(), 0))
+        return t_out
+
+    def sha3_fixed_dev(self, t_data, msg_len: int, stride: int, n: int, d: int, t_out, dev_index: int = 0):
+        self._check(self.lib.capy_sha3_batch_fixed_dev(self._ctx, dev_index, self._stream(), d, t_data.data_ptr(),
+                                                       msg_len, stride, n, t_out.data_ptr(), 0))
+        return t_out
+
+    def cshake_dev(self, t_data, t_off, out_bits: int, fn: bytes, custom: bytes, d: int, t_out, dev_index: int = 0):
+        n = t_off.numel() - 1
+        fn_a, cs_a = _u8(fn), _u8(custom)
+        self._check(self.lib.capy_cshake_batch_dev(self._ctx, dev_index, self._stream(), d, t_data.data_ptr(),
+                                                   t_off.data_ptr(), n, _hp(fn_a), len(fn_a), _hp(cs_a), len(cs_a),
+                                                   out_bits, t_out.data_ptr()))
+        return t_out
+
+    def kmac_xof_dev(self, t_keys, t_key_off, t_data, t_off, out_bits: int, custom: bytes, d: int, t_out,
+                     t_out_off=None, dev_index: int = 0):
+        n = t_off.numel() - 1
+        cs_a = _u8(custom)
+        self._check(self.lib.capy_kmac_xof_batch_dev(
+            self._ctx, dev_index, self._stream(), d, t_keys.data_ptr(), t_key_off.data_ptr(), t_data.data_ptr(),
+            t_off.data_ptr(), n, _hp(cs_a), len(cs_a), out_bits,
+            t_out_off.data_ptr() if t_out_off is not None else None, t_out.data_ptr()))
+        return t_out
+
+    def kmac_xof_fixed_dev(self, t_keys, key_len: int, key_stride: int, t_data, msg_len: int, msg_stride: int, n: int,
+                           out_bits: int, custom: bytes, d: int, t_out, dev_index: int = 0):
+        cs_a = _u8(custom)
+        self._check(self.lib.capy_kmac_xof_batch_fixed_dev(
+            self._ctx, dev_index, self._stream(), d, t_keys.data_ptr(), key_len, key_stride,
+            t_data.data_ptr() if t_data is not None else None, msg_len, msg_stride, n, _hp(cs_a), len(cs_a), out_bits,
+            t_out.data_ptr()))
+        return t_out
+
+    def fips_shake_dev(self, t_data, t_off, shake_bits: int, out_bytes: int, t_out, dev_index: int = 0):
+        n = t_off.numel() - 1
+        self._check(self.lib.capy_fips_shake_batch_dev(self._ctx, dev_index, self._stream(), shake_bits,
+                                                       t_data.data_ptr(), t_off.data_ptr(), n, out_bytes,
+                                                       t_out.data_ptr()))
+        return t_out
+
+    def ed448_fixed_base_dev(self, t_scalars, n: int, t_out, dev_index: int = 0):
+        self._check(self.lib.capy_ed448_fixed_base_batch_dev(self._ctx, dev_index, self._stream(),
+                                                             t_scalars.data_ptr(), n, t_out.data_ptr()))
+        return t_out
+
+    def ed448_var_base_dev(self, t_scalars, t_points, n: int, t_out, t_bad=None, dev_index: int = 0):
+        self._check(self.lib.capy_ed448_var_base_batch_dev(self._ctx, dev_index, self._stream(), t_scalars.data_ptr(),
+                                                           t_points.data_ptr(), n, t_out.data_ptr(),
+                                                           t_bad.data_ptr() if t_bad is not None else None))
+        return t_out
+
+    def ed448_keygen_dev(self, t_pws, t_pw_off, d: int, t_out, dev_index: int = 0):
+        n = t_pw_off.numel() - 1
+        self._check(self.lib.capy_ed448_keygen_batch_dev(self._ctx, dev_index, self._stream(), d, t_pws.data_ptr(),
+                                                         t_pw_off.data_ptr(), n, t_out.data_ptr()))
+        return t_out
+
+    def ed448_sign_dev(self, t_pws, t_pw_off, t_msgs, t_msg_off, d: int, t_h, t_z, dev_index: int = 0):
+        n = t_pw_off.numel() - 1
+        self._check(self.lib.capy_ed448_sign_batch_dev(self._ctx, dev_index, self._stream(), d, t_pws.data_ptr(),
+                                                       t_pw_off.data_ptr(), t_msgs.data_ptr(), t_msg_off.data_ptr(), n,
+                                                       t_h.data_ptr(), t_z.data_ptr()))
+
+    def ed448_verify_dev(self, t_pub, t_msgs, t_msg_off, t_h, t_z, d: int, t_ok, t_bad=None, dev_index: int = 0):
+        n = t_msg_off.numel() - 1
+        self._check(self.lib.capy_ed448_verify_batch_dev(self._ctx, dev_index, self._stream(), d, t_pub.data_ptr(),
+                                                         t_msgs.data_ptr(), t_msg_off.data_ptr(), t_h.data_ptr(),
+                                                         t_z.data_ptr(), n, t_ok.data_ptr(),
+                                                         t_bad.data_ptr() if t_bad is not None else None))
+        return t_ok
