@@ -14,7 +14,7 @@
 namespace capy {
 
 constexpr int kNumStreams = 3;
-constexpr int kNumScratch = 24;
+constexpr int kNumScratch = 56;  // 0..17 sponge entry points, 24..55 Ed448 pipelines
 
 // grow-only device scratch slots; each API call uses a fixed set of slot ids
 struct Scratch {

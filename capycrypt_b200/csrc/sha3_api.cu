@@ -9,6 +9,7 @@
 #include <thread>
 
 #include "internal.h"
+#include "hostbatch.h"
 #include "sponge.cuh"
 
 namespace capy {
@@ -288,94 +289,6 @@ int launch_kmac_xof(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t stream, const Kma
   J.out_bytes = a.out_bytes;
   J.n = a.n;
   return launch_sponge(ctx, stream, (int)(bytepad_value(a.d_bits) * 8 / 64), J);
-}
-
-// ---- host-buffer plumbing -----------------------------------------------------------------------
-// Splits items [0, n) across the ctx devices (contiguous ranges, balanced by bytes) and, inside a
-// device, into chunks that are copied in, processed and copied out on rotating streams so that
-// H2D, kernel and D2H of neighbouring chunks overlap.  No collective: items are independent.
-struct Range {
-  uint64_t i0, i1;
-};
-
-static std::vector<Range> split_items(const uint64_t* off, uint64_t fixed_len, uint64_t i0, uint64_t i1, size_t parts,
-                                      uint64_t per_item_cost) {
-  std::vector<Range> r;
-  if (i1 <= i0) return r;
-  parts = std::max<size_t>(1, std::min<uint64_t>(parts, i1 - i0));
-  auto cost_at = [&](uint64_t i) -> uint64_t {  // cumulative cost of items [i0, i)
-    uint64_t bytes = off ? off[i] - off[i0] : (i - i0) * fixed_len;
-    return bytes + (i - i0) * per_item_cost;
-  };
-  const uint64_t total = cost_at(i1);
-  uint64_t start = i0;
-  for (size_t p = 1; p <= parts && start < i1; p++) {
-    uint64_t end;
-    if (p == parts) {
-      end = i1;
-    } else {
-      const uint64_t target = total / parts * p;
-      uint64_t lo = start + 1, hi = i1;
-      while (lo < hi) {  // first index with cumulative cost >= target
-        uint64_t mid = (lo + hi) / 2;
-        if (cost_at(mid) < target) lo = mid + 1;
-        else hi = mid;
-      }
-      end = lo;
-    }
-    if (end > start) r.push_back({start, end});
-    start = end;
-  }
-  return r;
-}
-
-template <class F>
-static int for_each_device(capy_ctx* ctx, const std::vector<Range>& shards, F&& fn) {
-  if (shards.size() <= 1) {
-    if (shards.empty()) return CAPY_OK;
-    DeviceGuard g(ctx->devs[0].dev);
-    return fn(ctx->devs[0], shards[0]);
-  }
-  std::vector<int> rcs(shards.size(), CAPY_OK);
-  std::vector<std::thread> th;
-  for (size_t k = 0; k < shards.size(); k++)
-    th.emplace_back([&, k] {
-      cudaSetDevice(ctx->devs[k].dev);
-      rcs[k] = fn(ctx->devs[k], shards[k]);
-    });
-  for (auto& t : th) t.join();
-  for (int rc : rcs)
-    if (rc) return rc;
-  return CAPY_OK;
-}
-
-// one packed host input staged per chunk: bytes [a0, off[i1]) with a0 = off[i0] rounded down to 16
-struct StagedPacked {
-  const uint8_t* d_base;  // device pointer such that d_base + off[i] addresses item i
-  const uint64_t* d_off;  // device copy of off[i0 .. i1]
-};
-
-static int stage_packed(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t st, int slot_data, int slot_off, const uint8_t* data,
-                        const uint64_t* off, uint64_t i0, uint64_t i1, StagedPacked* out) {
-  const uint64_t a0 = off[i0] & ~(uint64_t)15, a1 = off[i1];
-  const size_t nbytes = (size_t)(a1 - a0);
-  uint8_t* d_data = (uint8_t*)scratch_get(dc, slot_data, nbytes + 16);
-  uint64_t* d_off = (uint64_t*)scratch_get(dc, slot_off, (size_t)(i1 - i0 + 1) * 8);
-  if (!d_data || !d_off) return CAPY_ERR_OOM;
-  if (nbytes) CAPY_CUDA(ctx, cudaMemcpyAsync(d_data, data + a0, nbytes, cudaMemcpyHostToDevice, st));
-  CAPY_CUDA(ctx, cudaMemcpyAsync(d_off, off + i0, (size_t)(i1 - i0 + 1) * 8, cudaMemcpyHostToDevice, st));
-  out->d_base = reinterpret_cast<const uint8_t*>(reinterpret_cast<uintptr_t>(d_data) - (uintptr_t)a0);
-  out->d_off = d_off;
-  return CAPY_OK;
-}
-
-constexpr uint64_t kChunkBytes = 16ull << 20;
-
-static size_t chunk_count(uint64_t bytes, uint64_t items) {
-  uint64_t c = (bytes + kChunkBytes - 1) / kChunkBytes;
-  c = std::max<uint64_t>(c, 1);
-  c = std::min<uint64_t>(c, std::max<uint64_t>(items / 1024, 1));
-  return (size_t)c;
 }
 
 }  // namespace capy
