@@ -1,0 +1,422 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the capyCRYPT B200 batch engine (contract: see the task brief).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--no-extras]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Metric (BASELINE.json): SHA3-256 GB/s (+ Ed448 scalar-mults/s in `extra`).  A step is one pass of the hot
+path over one batch: SHA3-256 (SecParam::D256) over 2^20 random 64-byte messages per GPU
+(BASELINE.json configs[0], the configuration the metric is quoted on).  Weak scaling: every rank hashes
+its own 2^20-message batch, no collective on the data path; `value` = bytes hashed by all ranks / max
+time over ranks.  Prints ONE JSON line on rank 0.
+
+The oracle (oracle/) is touched only by the cpu_baseline leg and by --impl reference.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_MSGS = 1 << 20
+MSG_LEN = 64
+DIGEST = 32
+N_ROT = 4  # rotating input/output buffers: 4 x (64 + 32) MiB = 384 MiB > 126 MB of L2
+OPS_PER_PERM = 4320  # 122 LOP3 + 58 SHF per round x 24
+MAC_FIXED = 2.03e5  # canonical 32x32->64 MAC budgets per scalar multiplication
+MAC_VAR = 7.12e5
+PEAK_FALLBACK = {"lop3": 18.52e12, "imad_wide": 8.67e12}  # profiles/r01_peaks_int_pipes.json
+
+
+def _env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+# ------------------------------------------------------------------------------------------------------
+# clocks: sample SM clock + throttle reasons DURING the timed region (NVML, same data as nvidia-smi)
+# ------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    def __init__(self, index: int, period_s: float = 0.02):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._t = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:  # pragma: no cover
+            self.nv, self.err = None, repr(e)
+        self.period = period_s
+
+    def _run(self):
+        nv = self.nv
+        names = {
+            nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+            nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+            nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+            nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+            nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake",
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, nm in names.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            self._stop.wait(self.period)
+
+    def start(self):
+        if self.nv:
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t:
+            self._t.join()
+        s = sorted(self.samples)
+        return {
+            "sm_mhz": s[len(s) // 2] if s else None,
+            "sm_max_mhz": self.max_mhz,
+            "reasons": sorted(self.reasons),
+            "samples": len(s),
+        }
+
+
+# ------------------------------------------------------------------------------------------------------
+# CPU baseline (oracle port) -- the ONLY place bench.py touches oracle/
+# ------------------------------------------------------------------------------------------------------
+def cpu_sha3_baseline(budget_s: float, threads: int = 0):
+    """Times the structure-faithful C restatement (oracle/ref_cpu.c, -march=native) of
+    Message::compute_sha3_hash looped over 64-byte messages on `threads` host threads (0 = all)."""
+    import numpy as np
+
+    from oracle import cpu
+
+    orc = cpu.get(native=True)
+    cores = orc.max_threads if threads <= 0 else threads
+    rng = np.random.default_rng(1)
+    n_cal = 1 << 16
+    buf = rng.integers(0, 256, size=n_cal * MSG_LEN, dtype=np.uint8)
+    off = np.arange(n_cal + 1, dtype=np.uint64) * MSG_LEN
+    orc.sha3_batch(buf, off, 256, threads=threads)  # warm
+    t0 = time.perf_counter()
+    orc.sha3_batch(buf, off, 256, threads=threads)
+    rate = n_cal / (time.perf_counter() - t0)
+    n = int(min(N_MSGS, max(n_cal, rate * budget_s)))
+    buf = rng.integers(0, 256, size=n * MSG_LEN, dtype=np.uint8)
+    off = np.arange(n + 1, dtype=np.uint64) * MSG_LEN
+    reps = max(1, int(rate * budget_s / n))
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        orc.sha3_batch(buf, off, 256, threads=threads)
+    dt = time.perf_counter() - t0
+    gbps = n * reps * MSG_LEN / dt / 1e9
+    return {
+        "value": gbps,
+        "unit": "GB/s",
+        "cores": cores,
+        "kind": "port",
+        "sample": f"{reps} x {n} messages x {MSG_LEN} B, SHA3-256, oracle/ref_cpu.c (C restatement of the reference's "
+                  f"Rust path incl. its message copy and extra permutation), gcc -O3 -march=native, {cores} threads",
+        "msgs_per_s": n * reps / dt,
+    }
+
+
+def run_reference(args, rank: int):
+    """--impl reference: the reference's own CPU implementation of the path on the host cores.  The Rust
+    reference cannot be built in this image (no rustc/cargo), so this is the oracle port."""
+    if rank != 0:
+        return
+    import numpy as np
+
+    from oracle import cpu
+
+    orc = cpu.get(native=True)
+    cores = orc.max_threads
+    rng = np.random.default_rng(1)
+    n_cal = 1 << 16
+    buf = rng.integers(0, 256, size=n_cal * MSG_LEN, dtype=np.uint8)
+    off = np.arange(n_cal + 1, dtype=np.uint64) * MSG_LEN
+    orc.sha3_batch(buf, off, 256, threads=0)
+    t0 = time.perf_counter()
+    orc.sha3_batch(buf, off, 256, threads=0)
+    rate = n_cal / (time.perf_counter() - t0)
+    total_budget_s = 90.0
+    n = int(min(N_MSGS, max(4096, rate * total_budget_s / max(1, args.steps + args.warmup))))
+    buf = rng.integers(0, 256, size=n * MSG_LEN, dtype=np.uint8)
+    off = np.arange(n + 1, dtype=np.uint64) * MSG_LEN
+    for _ in range(args.warmup):
+        orc.sha3_batch(buf, off, 256, threads=0)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        orc.sha3_batch(buf, off, 256, threads=0)
+    dt = time.perf_counter() - t0
+    gbps = n * args.steps * MSG_LEN / dt / 1e9
+    sample = (f"each step = {n} of the {N_MSGS} messages x {MSG_LEN} B (bounded sample), oracle/ref_cpu.c restatement of "
+              f"Message::compute_sha3_hash looped, gcc -O3 -march=native, {cores} threads")
+    line = {
+        "impl": "reference", "metric": "sha3_256_GBps", "value": gbps, "unit": "GB/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": "sha3_256_2^20x64B", "msgs_per_step": n, "msg_bytes": MSG_LEN},
+        "cpu_baseline": {"value": gbps, "unit": "GB/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": gbps, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------
+def live_peaks():
+    """Integer-pipe peaks measured now on this GPU by the in-tree microbenchmark (csrc/peaks.cu)."""
+    exe = os.path.join(ROOT, "capycrypt_b200", "_lib", "peaks")
+    try:
+        r = subprocess.run([exe, "600"], capture_output=True, text=True, timeout=120)
+        d = json.loads(r.stdout.strip().splitlines()[-1])
+        return {"lop3": d["lop3"]["thread_ops_per_s"], "imad_wide": d["imad_wide"]["thread_ops_per_s"],
+                "source": "measured live by capycrypt_b200/_lib/peaks (csrc/peaks.cu)"}
+    except Exception as e:
+        return {**PEAK_FALLBACK, "source": f"profiles/r01_peaks_int_pipes.json (live run failed: {e!r})"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-extras", action="store_true", help="skip the Ed448 / KMAC side measurements")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank, world, local = _env_int("RANK", 0), _env_int("WORLD_SIZE", 1), _env_int("LOCAL_RANK", 0)
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import numpy as np
+    import torch
+
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+
+        dist = dist_mod
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
+    from capycrypt_b200 import Engine
+
+    eng = Engine()  # one ctx on this rank's GPU
+    dev = torch.device("cuda", local)
+    g = torch.Generator(device=dev)
+    g.manual_seed(1 + rank)
+    ins = [torch.randint(0, 256, (N_MSGS * MSG_LEN,), dtype=torch.uint8, device=dev, generator=g) for _ in range(N_ROT)]
+    outs = [torch.zeros(N_MSGS * DIGEST, dtype=torch.uint8, device=dev) for _ in range(N_ROT)]
+
+    def step(i):
+        eng.sha3_fixed_dev(ins[i % N_ROT], MSG_LEN, MSG_LEN, N_MSGS, 256, outs[i % N_ROT])
+
+    peaks = live_peaks() if rank == 0 else PEAK_FALLBACK
+    for i in range(args.warmup):
+        step(i)
+    torch.cuda.synchronize()
+    # sanity (not the oracle): SHA3-256 is FIPS-exact in the reference for every length
+    import hashlib
+
+    m0 = ins[0][:MSG_LEN].cpu().numpy().tobytes()
+    assert outs[0][:DIGEST].cpu().numpy().tobytes() == hashlib.sha3_256(m0).digest(), "digest mismatch"
+
+    sampler = ClockSampler(local)
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize()
+    launches0 = eng.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.start()
+    e0.record()
+    for i in range(args.steps):
+        step(i)
+    e1.record()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    if dist:
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+    launches = eng.launch_count - launches0
+    if dist:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = world * N_MSGS * MSG_LEN / (ms_per_step * 1e-3) / 1e9
+
+    # ---- e2e: the same metric through the host-buffer C entry point (pinned host memory, H2D + D2H inside) ----
+    k_e2e = max(5, min(args.steps, 100))
+    h_in = eng.pinned(N_MSGS * MSG_LEN)
+    h_out = eng.pinned(N_MSGS * DIGEST)
+    h_in[:] = ins[0].cpu().numpy()
+    h_out2d = h_out.reshape(N_MSGS, DIGEST)
+    for _ in range(3):
+        eng.sha3_fixed(h_in, MSG_LEN, MSG_LEN, N_MSGS, 256, out=h_out2d)
+    if dist:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(k_e2e):
+        eng.sha3_fixed(h_in, MSG_LEN, MSG_LEN, N_MSGS, 256, out=h_out2d)
+    e2e_s = time.perf_counter() - t0
+    if dist:
+        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    assert h_out[:DIGEST].tobytes() == hashlib.sha3_256(m0).digest()
+    e2e = {"value": world * N_MSGS * MSG_LEN * k_e2e / e2e_s / 1e9, "unit": "GB/s",
+           "h2d_bytes_per_step": N_MSGS * MSG_LEN, "d2h_bytes_per_step": N_MSGS * DIGEST, "steps": k_e2e,
+           "ms_per_step": e2e_s / k_e2e * 1e3,
+           "api": "capy_sha3_batch_fixed (host buffers from capy_host_alloc, chunked H2D/kernel/D2H on 3 streams)"}
+
+    # ---- roofline of the dominant kernel (sha3_uniform_kernel<17>: one launch per step) ----
+    ops = N_MSGS * OPS_PER_PERM
+    achieved = ops / (ms_per_step * 1e-3) * (1 if world == 1 else 1)  # per GPU
+    hbm_bytes = N_MSGS * (MSG_LEN + DIGEST)
+    try:
+        hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+        hbm_src = "MEASURED_PEAKS.json"
+    except Exception:
+        hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("sha3_uniform_kernel<17>")
+    except Exception:
+        pass
+    roofline = {
+        "bound": "int_alu", "kernel": "sha3_uniform_kernel<17>", "achieved": achieved / 1e12, "peak": peaks["lop3"] / 1e12,
+        "unit": "Tint32op/s", "frac": achieved / peaks["lop3"], "traffic": traffic,
+        "peak_source": peaks.get("source", "profiles/r01_peaks_int_pipes.json"),
+        "algorithmic": f"{OPS_PER_PERM} int32 LOP3/SHF per Keccak-f[1600] x 1 permutation x {N_MSGS} messages per launch",
+        "hbm": {"achieved": hbm_bytes / (ms_per_step * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                "frac": hbm_bytes / (ms_per_step * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src,
+                "algorithmic": "64 B in + 32 B out per message"},
+        "note": "the path is integer-ALU bound (BASELINE.md 4): the binding roofline is the measured LOP3/SHF pipe peak, "
+                "the HBM fraction is reported beside it",
+    }
+
+    line = {
+        "metric": "sha3_256_GBps", "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": "sha3_256_2^20x64B", "per_gpu_msgs": N_MSGS, "msg_bytes": MSG_LEN, "sec_param": "D256",
+                   "l2": f"inputs/outputs rotate over {N_ROT} buffer pairs (384 MiB per GPU > 126 MB L2)",
+                   "sharding": "one 2^20-message batch per rank, no collective"},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
+        "msgs_per_s": world * N_MSGS / (ms_per_step * 1e-3),
+    }
+
+    if not args.no_extras:
+        line["extra"] = extras(eng, dev, peaks, world, dist, rank)
+    if rank == 0 and world == 1 and not args.no_cpu:
+        line["cpu_baseline"] = cpu_sha3_baseline(budget_s=1.5)
+    elif rank == 0:
+        line["cpu_baseline"] = None
+    eng.close()
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+
+
+def extras(eng, dev, peaks, world, dist, rank):
+    """Side measurements for the other BASELINE.json configs (device-resident, CUDA events, max over ranks)."""
+    import torch
+
+    def timed(fn, steps, warmup=2):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        if dist:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    g = torch.Generator(device=dev)
+    g.manual_seed(100 + rank)
+    rnd = lambda n: torch.randint(0, 256, (n,), dtype=torch.uint8, device=dev, generator=g)
+    out = {}
+
+    # cfg 2: KMACXOF256 (D512) over 2^16 x 4 KB messages, 32-byte keys, 512-bit output
+    n2, mlen = 1 << 16, 4096
+    data, keys = rnd(n2 * mlen), rnd(n2 * 32)
+    o = torch.zeros(n2 * 64, dtype=torch.uint8, device=dev)
+    ms = timed(lambda: eng.kmac_xof_fixed_dev(keys, 32, 32, data, mlen, mlen, n2, 512, b"My Tagged Application", 512, o), 10)
+    perms = 32  # 33 absorbed blocks, the constant prefix block is cached
+    out["kmac256_2^16x4KB"] = {
+        "GBps": world * n2 * mlen / (ms * 1e-3) / 1e9, "ms_per_step": ms,
+        "frac_int_alu": n2 * perms * OPS_PER_PERM / (ms * 1e-3) / peaks["lop3"], "perms_per_msg": perms}
+
+    # cfg 3: Ed448 fixed-base [s]G for 2^20 scalars
+    n3 = 1 << 20
+    sc = rnd(n3 * 56)
+    pts = torch.zeros(n3 * 112, dtype=torch.uint8, device=dev)
+    ms = timed(lambda: eng.ed448_fixed_base_dev(sc, n3, pts), 3, 1)
+    rate = n3 / (ms * 1e-3)
+    out["ed448_fixed_base_2^20"] = {
+        "scalar_mults_per_s": world * rate, "ms_per_step": ms, "frac_imad_wide": rate * MAC_FIXED / peaks["imad_wide"],
+        "canonical_macs": MAC_FIXED, "constant_time_lookup": True}
+
+    # variable base for 2^18 (scalar, point) pairs
+    n4 = 1 << 18
+    o4 = torch.zeros(n4 * 112, dtype=torch.uint8, device=dev)
+    ms = timed(lambda: eng.ed448_var_base_dev(sc, pts, n4, o4), 2, 1)
+    rate = n4 / (ms * 1e-3)
+    out["ed448_var_base_2^18"] = {
+        "scalar_mults_per_s": world * rate, "ms_per_step": ms, "frac_imad_wide": rate * MAC_VAR / peaks["imad_wide"],
+        "canonical_macs": MAC_VAR, "constant_time_lookup": True}
+
+    # cfg 4: Schnorr sign + verify, 2^18 x (32-byte password, 256-byte message), D512
+    pw, msg = rnd(n4 * 32), rnd(n4 * 256)
+    pw_off = torch.arange(n4 + 1, dtype=torch.int64, device=dev) * 32
+    msg_off = torch.arange(n4 + 1, dtype=torch.int64, device=dev) * 256
+    h = torch.zeros(n4 * 56, dtype=torch.uint8, device=dev)
+    z = torch.zeros(n4 * 56, dtype=torch.uint8, device=dev)
+    pub = torch.zeros(n4 * 112, dtype=torch.uint8, device=dev)
+    ok = torch.zeros(n4, dtype=torch.uint8, device=dev)
+    ms_k = timed(lambda: eng.ed448_keygen_dev(pw, pw_off, 512, pub), 2, 1)
+    ms_s = timed(lambda: eng.ed448_sign_dev(pw, pw_off, msg, msg_off, 512, h, z), 2, 1)
+    ms_v = timed(lambda: eng.ed448_verify_dev(pub, msg, msg_off, h, z, 512, ok), 2, 1)
+    assert bool(ok.all().item()), "engine rejected its own signatures"
+    out["ed448_schnorr_2^18x256B"] = {
+        "keygens_per_s": world * n4 / (ms_k * 1e-3), "signs_per_s": world * n4 / (ms_s * 1e-3),
+        "verifies_per_s": world * n4 / (ms_v * 1e-3), "ms_keygen": ms_k, "ms_sign": ms_s, "ms_verify": ms_v}
+    return out
+
+
+if __name__ == "__main__":
+    main()
