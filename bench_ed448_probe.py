@@ -1,9 +1,9 @@
-# quick device-resident throughput probe (development aid, not the contract bench)
-import sys, time, json
+# development aid (not the contract bench): device-resident Ed448 throughput of one library variant.
+# usage: CAPY_GPU_LIB=<path> python bench_ed448_probe.py
+import hashlib, json, os, sys
 import numpy as np, torch
 from capycrypt_b200 import Engine
 eng = Engine()
-res = {}
 def timeit(fn, reps=3):
     fn(); torch.cuda.synchronize()
     best = 1e9
@@ -12,15 +12,17 @@ def timeit(fn, reps=3):
         e0.record(); fn(); e1.record(); torch.cuda.synchronize()
         best = min(best, e0.elapsed_time(e1))
     return best
-for logn in (16, 18, 20):
-    n = 1 << logn
-    sc = torch.randint(0, 256, (n * 56,), dtype=torch.uint8, device="cuda")
-    out = torch.zeros(n * 112, dtype=torch.uint8, device="cuda")
-    ms = timeit(lambda: eng.ed448_fixed_base_dev(sc, n, out))
-    res[f"fixed_base_2^{logn}"] = {"ms": ms, "Mops": n / ms / 1e3}
-    if logn <= 18:
-        pts = out.clone()
-        out2 = torch.zeros(n * 112, dtype=torch.uint8, device="cuda")
-        ms = timeit(lambda: eng.ed448_var_base_dev(sc, pts, n, out2))
-        res[f"var_base_2^{logn}"] = {"ms": ms, "Mops": n / ms / 1e3}
-print(json.dumps(res, indent=1))
+g = torch.Generator(device="cuda"); g.manual_seed(7)
+res = {"lib": os.path.basename(os.environ.get("CAPY_GPU_LIB", "default"))}
+n = 1 << 20
+sc = torch.randint(0, 256, (n * 56,), dtype=torch.uint8, device="cuda", generator=g)
+out = torch.zeros(n * 112, dtype=torch.uint8, device="cuda")
+ms = timeit(lambda: eng.ed448_fixed_base_dev(sc, n, out))
+res["fixed_2^20_ms"] = round(ms, 3); res["fixed_Mps"] = round(n / ms / 1e3, 2)
+res["fixed_digest"] = hashlib.sha256(out[: 112 * 4096].cpu().numpy().tobytes()).hexdigest()[:12]
+n2 = 1 << 18
+out2 = torch.zeros(n2 * 112, dtype=torch.uint8, device="cuda")
+ms = timeit(lambda: eng.ed448_var_base_dev(sc, out, n2, out2), reps=2)
+res["var_2^18_ms"] = round(ms, 3); res["var_Mps"] = round(n2 / ms / 1e3, 2)
+res["var_digest"] = hashlib.sha256(out2[: 112 * 4096].cpu().numpy().tobytes()).hexdigest()[:12]
+print(json.dumps(res))

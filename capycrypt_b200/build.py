@@ -18,6 +18,10 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "_lib")
 LIB = os.path.join(LIBDIR, "libcapycrypt_gpu.so")
 SOURCES = ["ctx.cu", "sha3_api.cu", "ed448_api.cu", "ed448_fixed.cu", "ed448_var.cu"]
+# per-source tuning, from measurements on B200 (profiles/README.md): the variable-base ladder is instruction-
+# cache bound when fully inlined (432 KB of code), so its field multiplications are out-of-line calls and
+# the kernel is capped at 128 registers (4 blocks/SM); the fixed-base comb is fastest fully inlined.
+PER_SOURCE_DEFINES = {"ed448_var.cu": ["-DCAPY_FE_OOL", "-DCAPY_ED_MINBLOCKS=4"]}
 NVCC = os.environ.get("NVCC", "nvcc")
 BASE_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -35,6 +39,7 @@ def _stamp(defines):
         h.update(p.encode())
         h.update(open(p, "rb").read())
     h.update(" ".join(BASE_FLAGS + defines).encode())
+    h.update(repr(sorted(PER_SOURCE_DEFINES.items())).encode())
     return h.hexdigest()
 
 
@@ -50,7 +55,8 @@ def build(force: bool = False, defines=(), verbose: bool = False, lib: str = LIB
 
     def compile_one(src):
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
-        cmd = [NVCC, *BASE_FLAGS, *defines, "-Xptxas", "-v", "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [NVCC, *BASE_FLAGS, *PER_SOURCE_DEFINES.get(src, []), *defines, "-Xptxas", "-v", "-c",
+               os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")

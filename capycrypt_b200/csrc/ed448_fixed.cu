@@ -1,6 +1,9 @@
 // ed448_fixed.cu -- fixed-base scalar multiplication [k]G: comb table of G built once per device,
 // then 112 mixed additions per item (the reference has no fixed-base path: `generator() * s` runs the
 // generic Mul<Scalar>, ecc/keypair.rs:44; the result is the same curve point).
+#ifndef CAPY_ED_MINBLOCKS
+#define CAPY_ED_MINBLOCKS 1
+#endif
 #include "ed448_kernels.h"
 
 namespace capy {
@@ -23,7 +26,7 @@ __global__ void fb_table_kernel(uint32_t* table) {
 }
 
 // r_i = [k_i]G, k_i reduced scalars in SoA words; result stored extended (X, Y, Z, T)
-__global__ void __launch_bounds__(128) fixed_base_kernel(const uint32_t* __restrict__ k_words,
+__global__ void __launch_bounds__(128, CAPY_ED_MINBLOCKS) fixed_base_kernel(const uint32_t* __restrict__ k_words,
                                                          const uint32_t* __restrict__ table,
                                                          uint32_t* __restrict__ proj, uint64_t n, int constant_time) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -1,12 +1,15 @@
 // ed448_var.cu -- variable-base scalar multiplication [k]P (ecc/signable.rs:77 `*pub_key * h_scalar`,
 // ecc/encryptable.rs:37,78): per-item table 1P..8P in local memory, signed radix-16 fixed window.
+#ifndef CAPY_ED_MINBLOCKS
+#define CAPY_ED_MINBLOCKS 1
+#endif
 #include "ed448_kernels.h"
 
 namespace capy {
 
 // r_i = [k_i]P_i (+ addend_i).  scalars: 56-byte big-endian, exact integers (mode4 = 0) or
 // 4 * BE mod r (mode4 = 1, ECDH: ecc/encryptable.rs:36).  Off-curve P_i -> bad[i] = 1, identity out.
-__global__ void __launch_bounds__(128) var_base_kernel(const uint8_t* __restrict__ scalars_be56, int mode4,
+__global__ void __launch_bounds__(128, CAPY_ED_MINBLOCKS) var_base_kernel(const uint8_t* __restrict__ scalars_be56, int mode4,
                                                        const uint8_t* __restrict__ points_xy,
                                                        const uint32_t* __restrict__ addend /* ext SoA or null */,
                                                        uint32_t* __restrict__ proj, uint8_t* __restrict__ bad, uint64_t n,

@@ -121,7 +121,7 @@ CAPY_HD uint64_t mulu(uint32_t a, uint32_t b) { return (uint64_t)a * b; }
 CAPY_HD uint64_t muls(int32_t na, uint32_t b) { return (uint64_t)((int64_t)na * (int64_t)(int32_t)b); }
 
 // r = a * b.  Requires alpha_a * alpha_b <= 6 (and each alpha < 8).  r may alias a or b.
-CAPY_HD void fe_mul(Fe& r, const Fe& a, const Fe& b) {
+CAPY_HD void fe_mul_inl(Fe& r, const Fe& a, const Fe& b) {
   uint32_t a0[8], a1[8], b0[8], b1[8], s[8], t[8];
   int32_t na0[8];
 #pragma unroll
@@ -161,7 +161,7 @@ CAPY_HD void fe_mul(Fe& r, const Fe& a, const Fe& b) {
 }
 
 // r = a^2.  Requires alpha_a^2 <= 6.
-CAPY_HD void fe_sqr(Fe& r, const Fe& a) {
+CAPY_HD void fe_sqr_inl(Fe& r, const Fe& a) {
   uint32_t a0[8], a1[8], s[8], d0[8], d1[8], ds[8];
   int32_t nd0[8], na0[8];
 #pragma unroll
@@ -223,14 +223,24 @@ CAPY_HD void fe_sqr(Fe& r, const Fe& a) {
   fe_carry_wide(r, R);
 }
 
-// out-of-line copies for cold code (inversion chain, table construction, point validation):
-// one body instead of ~450 inlined instructions per call site
+// out-of-line copies: one body instead of ~450 inlined instructions per call site.  Always used by
+// cold code (inversion chain, table construction, point validation); with CAPY_FE_OOL defined the hot
+// point arithmetic calls them too, which keeps the scalar-multiplication loops inside the instruction
+// cache and the kernels at <= 128 registers (operands then live in local memory / L1).
 #if defined(__CUDACC__)
 __host__ __device__ __noinline__
 #endif
 static void fe_mul_call(Fe* r, const Fe* a, const Fe* b) {
   Fe t;
-  fe_mul(t, *a, *b);
+  fe_mul_inl(t, *a, *b);
+  fe_copy(*r, t);
+}
+#if defined(__CUDACC__)
+__host__ __device__ __noinline__
+#endif
+static void fe_sqr_call(Fe* r, const Fe* a) {
+  Fe t;
+  fe_sqr_inl(t, *a);
   fe_copy(*r, t);
 }
 #if defined(__CUDACC__)
@@ -238,11 +248,19 @@ __host__ __device__ __noinline__
 #endif
 static void fe_sqrn_call(Fe* r, const Fe* a, int n) {
   Fe t;
-  fe_sqr(t, *a);
+  fe_sqr_inl(t, *a);
 #pragma unroll 1
-  for (int i = 1; i < n; i++) fe_sqr(t, t);
+  for (int i = 1; i < n; i++) fe_sqr_inl(t, t);
   fe_copy(*r, t);
 }
+
+#if defined(CAPY_FE_OOL)
+CAPY_HD void fe_mul(Fe& r, const Fe& a, const Fe& b) { fe_mul_call(&r, &a, &b); }
+CAPY_HD void fe_sqr(Fe& r, const Fe& a) { fe_sqr_call(&r, &a); }
+#else
+CAPY_HD void fe_mul(Fe& r, const Fe& a, const Fe& b) { fe_mul_inl(r, a, b); }
+CAPY_HD void fe_sqr(Fe& r, const Fe& a) { fe_sqr_inl(r, a); }
+#endif
 
 // r = a^(p-2) = 1/a (0 -> 0).  p - 2 = [223 ones][0][222 ones][0][1]  
 CAPY_HD void fe_inv(Fe& r, const Fe& x) {

@@ -111,9 +111,31 @@ __global__ void prefix_state_kernel(const uint8_t* prefix, uint32_t nblocks, uin
 
 static inline unsigned grid_for(uint64_t n, unsigned block) { return (unsigned)((n + block - 1) / block); }
 
-static int launch_sponge(capy_ctx* ctx, cudaStream_t stream, int lanes, const SpongeJob& J) {
+// Block size for a one-thread-per-item kernel: with few items (cfg 2 has 2^16) the grid is about one wave,
+// and the time is set by the SM that received the most blocks.  Pick the block size whose block count
+// spreads most evenly over the SMs (ties go to the larger block).
+static unsigned pick_block(uint64_t n, int sm_count, int threads_per_sm) {
+  unsigned best = 128;
+  double best_eff = -1.0;
+  for (unsigned bs : {128u, 64u, 32u}) {
+    const uint64_t blocks = (n + bs - 1) / bs;
+    const uint64_t slots = (uint64_t)sm_count * (threads_per_sm / bs);  // resident blocks per wave
+    const uint64_t waves = (blocks + slots - 1) / slots;
+    // work of the busiest SM relative to a perfectly even spread
+    const double per_sm = (double)blocks / sm_count;
+    const double busiest = waves > 1 ? (double)waves * (threads_per_sm / bs) : (double)((blocks + sm_count - 1) / sm_count);
+    const double eff = per_sm / busiest;
+    if (eff > best_eff + 0.02) {
+      best_eff = eff;
+      best = bs;
+    }
+  }
+  return best;
+}
+
+static int launch_sponge(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t stream, int lanes, const SpongeJob& J) {
   if (J.n == 0) return CAPY_OK;
-  const unsigned block = 128, grid = grid_for(J.n, block);
+  const unsigned block = pick_block(J.n, dc.sm_count, 512), grid = grid_for(J.n, block);
   switch (lanes) {
     case 9: sponge_kernel<9><<<grid, block, 0, stream>>>(J); break;
     case 13: sponge_kernel<13><<<grid, block, 0, stream>>>(J); break;
@@ -135,7 +157,7 @@ static SpongeJob empty_job() {
 }
 
 // ---- SHA3-d ------------------------------------------------------------------------------------
-static int launch_sha3(capy_ctx* ctx, cudaStream_t stream, int d, const uint8_t* data, const uint64_t* off,
+static int launch_sha3(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t stream, int d, const uint8_t* data, const uint64_t* off,
                        uint64_t msg_len, uint64_t stride, uint64_t n, uint8_t* out) {
   if (!valid_secparam(d)) return CAPY_ERR_BAD_SECPARAM;
   if (n == 0) return CAPY_OK;
@@ -166,7 +188,7 @@ static int launch_sha3(capy_ctx* ctx, cudaStream_t stream, int d, const uint8_t*
   J.out_stride = J.out_bytes = (uint64_t)d / 8;
   J.sq_lanes = (1600 - d) / 64;  // Rate::from(&d), sponge.rs:27 (first d/8 bytes are all that is kept)
   J.n = n;
-  return launch_sponge(ctx, stream, lanes, J);
+  return launch_sponge(ctx, dc, stream, lanes, J);
 }
 
 // ---- cSHAKE / KMAC prefix -----------------------------------------------------------------------
@@ -260,7 +282,7 @@ static int launch_cshake(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t stream, int 
   J.out = out;
   J.out_stride = J.out_bytes = out_bits / 8;
   J.n = n;
-  return launch_sponge(ctx, stream, (int)(bytepad_value(d) * 8 / 64), J);
+  return launch_sponge(ctx, dc, stream, (int)(bytepad_value(d) * 8 / 64), J);
 }
 
 int launch_kmac_xof(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t stream, const KmacDevArgs& a) {
@@ -288,7 +310,7 @@ int launch_kmac_xof(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t stream, const Kma
   J.out_stride = a.out_stride;
   J.out_bytes = a.out_bytes;
   J.n = a.n;
-  return launch_sponge(ctx, stream, (int)(bytepad_value(a.d_bits) * 8 / 64), J);
+  return launch_sponge(ctx, dc, stream, (int)(bytepad_value(a.d_bits) * 8 / 64), J);
 }
 
 }  // namespace capy
@@ -305,7 +327,7 @@ int capy_sha3_batch_dev(capy_ctx* ctx, int dev_index, void* stream, int d_bits, 
   if (!ctx || dev_index < 0 || dev_index >= (int)ctx->devs.size() || (n && (!d_data || !d_off || !d_digests)))
     return CAPY_ERR_BAD_ARG;
   DeviceGuard g(ctx->devs[dev_index].dev);
-  return launch_sha3(ctx, (cudaStream_t)stream, d_bits, d_data, d_off, 0, 0, n, d_digests);
+  return launch_sha3(ctx, ctx->devs[dev_index], (cudaStream_t)stream, d_bits, d_data, d_off, 0, 0, n, d_digests);
 }
 
 int capy_sha3_batch_fixed_dev(capy_ctx* ctx, int dev_index, void* stream, int d_bits, const uint8_t* d_data,
@@ -313,7 +335,7 @@ int capy_sha3_batch_fixed_dev(capy_ctx* ctx, int dev_index, void* stream, int d_
   if (!ctx || dev_index < 0 || dev_index >= (int)ctx->devs.size() || (n && (!d_data || !d_digests)) || stride < msg_len)
     return CAPY_ERR_BAD_ARG;
   DeviceGuard g(ctx->devs[dev_index].dev);
-  return launch_sha3(ctx, (cudaStream_t)stream, d_bits, d_data, nullptr, msg_len, stride, n, d_digests);
+  return launch_sha3(ctx, ctx->devs[dev_index], (cudaStream_t)stream, d_bits, d_data, nullptr, msg_len, stride, n, d_digests);
 }
 
 int capy_sha3_batch(capy_ctx* ctx, int d_bits, const uint8_t* data, const uint64_t* off, uint64_t n, uint8_t* digests,
@@ -335,7 +357,7 @@ int capy_sha3_batch(capy_ctx* ctx, int d_bits, const uint8_t* data, const uint64
       if (rc) return rc;
       uint8_t* d_out = (uint8_t*)scratch_get(dc, 3 * s + 2, (size_t)(ch.i1 - ch.i0) * ob);
       if (!d_out) return CAPY_ERR_OOM;
-      rc = launch_sha3(ctx, st, d_bits, sp.d_base, sp.d_off, 0, 0, ch.i1 - ch.i0, d_out);
+      rc = launch_sha3(ctx, dc, st, d_bits, sp.d_base, sp.d_off, 0, 0, ch.i1 - ch.i0, d_out);
       if (rc) return rc;
       CAPY_CUDA(ctx, cudaMemcpyAsync(digests + ch.i0 * ob, d_out, (size_t)(ch.i1 - ch.i0) * ob, cudaMemcpyDeviceToHost, st));
     }
@@ -367,7 +389,7 @@ int capy_sha3_batch_fixed(capy_ctx* ctx, int d_bits, const uint8_t* data, uint64
       uint8_t* d_out = (uint8_t*)scratch_get(dc, 3 * s + 2, (size_t)cnt * ob);
       if (!d_in || !d_out) return CAPY_ERR_OOM;
       CAPY_CUDA(ctx, cudaMemcpyAsync(d_in, data + ch.i0 * stride, in_bytes, cudaMemcpyHostToDevice, st));
-      int rc = launch_sha3(ctx, st, d_bits, d_in, nullptr, msg_len, stride, cnt, d_out);
+      int rc = launch_sha3(ctx, dc, st, d_bits, d_in, nullptr, msg_len, stride, cnt, d_out);
       if (rc) return rc;
       CAPY_CUDA(ctx, cudaMemcpyAsync(digests + ch.i0 * ob, d_out, (size_t)cnt * ob, cudaMemcpyDeviceToHost, st));
     }
@@ -552,7 +574,7 @@ int capy_fips_shake_batch_dev(capy_ctx* ctx, int dev_index, void* stream, int sh
   J.out = d_out;
   J.out_stride = J.out_bytes = out_bytes;
   J.n = n;
-  return launch_sponge(ctx, (cudaStream_t)stream, (int)J.rate / 8, J);
+  return launch_sponge(ctx, ctx->devs[dev_index], (cudaStream_t)stream, (int)J.rate / 8, J);
 }
 
 }  // extern "C"

@@ -242,7 +242,7 @@ __device__ __forceinline__ void sponge_item(const SpongeJob& J, uint64_t i) {
 }
 
 template <int LANES>
-__global__ void __launch_bounds__(128) sponge_kernel(const SpongeJob J) {
+__global__ void __launch_bounds__(128, 4) sponge_kernel(const SpongeJob J) {
   const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= J.n) return;
   sponge_item<LANES>(J, J.order ? (uint64_t)J.order[t] : t);

@@ -27,5 +27,16 @@ def build(force: bool = False) -> None:
                         "-o", exe, src], check=True)
 
 
+    # C++ host mirror check (links the product library; runs only on a GPU box)
+    root = os.path.join(HERE, "..", "..")
+    libdir = os.path.join(root, "capycrypt_b200", "_lib")
+    exe = os.path.join(OUT, "host_mirror_check")
+    src = os.path.join(HERE, "host_mirror_check.cpp")
+    hdrs = [os.path.join(root, "capycrypt_b200", "host", "capycrypt_gpu.hpp"), os.path.join(root, "include", "capy_gpu.h")]
+    if os.path.exists(os.path.join(libdir, "libcapycrypt_gpu.so")) and stale(exe, hdrs + [src]):
+        subprocess.run(["g++", "-O2", "-std=c++17", "-o", exe, src, "-L" + libdir, "-lcapycrypt_gpu",
+                        "-Wl,-rpath," + os.path.abspath(libdir)], check=True)
+
+
 if __name__ == "__main__":
     build()
