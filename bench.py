@@ -381,6 +381,41 @@ def extras(eng, dev, peaks, world, dist, rank):
         "GBps": world * n2 * mlen / (ms * 1e-3) / 1e9, "ms_per_step": ms,
         "frac_int_alu": n2 * perms * OPS_PER_PERM / (ms * 1e-3) / peaks["lop3"], "perms_per_msg": perms}
 
+    # cfg 5: mixed-size SHA3-512, lengths log-uniform in [64 B, 1 MiB], 16 GiB in total (strong scaling: the
+    # 16 GiB are split over the ranks); longest-message-first schedule, one thread per message
+    import numpy as np
+
+    rs = np.random.default_rng(5)
+    total = (16 << 30) // world
+    lens, acc = [], 0
+    while acc < total * world:
+        c = np.exp(rs.uniform(np.log(64), np.log(1 << 20), size=8192)).astype(np.int64)
+        lens.append(c)
+        acc += int(c.sum())
+    lens = np.concatenate(lens)
+    lens = lens[: int(np.searchsorted(np.cumsum(lens), total * world)) + 1][rank::world]  # this rank's share
+    off5 = np.zeros(len(lens) + 1, np.int64)
+    off5[1:] = np.cumsum(lens)
+    nbytes5 = int(off5[-1])
+    d5 = torch.empty(nbytes5 + 8, dtype=torch.uint8, device=dev)
+    d5.random_(0, 256, generator=g)
+    t_off5 = torch.from_numpy(off5).to(dev)
+    o5 = torch.zeros(len(lens) * 64, dtype=torch.uint8, device=dev)
+    ms = timed(lambda: eng.sha3_dev(d5, t_off5, 512, o5), 2, 1)
+    perms5 = int(((lens + 1 + 71) // 72).sum())
+    tot_bytes = torch.tensor([float(nbytes5)], device=dev, dtype=torch.float64)
+    tot_perms = torch.tensor([float(perms5)], device=dev, dtype=torch.float64)
+    if dist:
+        dist.all_reduce(tot_bytes)
+        dist.all_reduce(tot_perms)
+    out["sha3_512_mixed_16GiB"] = {
+        "GBps": float(tot_bytes.item()) / (ms * 1e-3) / 1e9, "ms_per_step": ms, "msgs_this_rank": int(len(lens)),
+        "frac_int_alu": float(tot_perms.item()) / world * OPS_PER_PERM / (ms * 1e-3) / peaks["lop3"],
+        "scaling": "strong", "longest_chain_perms": int((lens.max() + 1 + 71) // 72),
+        "note": "a sponge is sequential per message: the step cannot be shorter than the longest message's chain "
+                "(1 MiB = 14 564 permutations ~ 71 ms on one scheduler)"}
+    del d5, o5, t_off5
+
     # cfg 3: Ed448 fixed-base [s]G for 2^20 scalars
     n3 = 1 << 20
     sc = rnd(n3 * 56)

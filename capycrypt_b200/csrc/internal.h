@@ -94,6 +94,7 @@ struct KmacDevArgs {
   const uint64_t* out_off;
   uint64_t out_stride;
   uint8_t* out;
+  bool no_sort = false;  // keep the caller's order (skips the length bucketing and its tiny D2H sync)
 };
 int launch_kmac_xof(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t stream, const KmacDevArgs& a);
 

@@ -111,8 +111,135 @@ __global__ void prefix_state_kernel(const uint8_t* prefix, uint32_t nblocks, uin
 
 static inline unsigned grid_for(uint64_t n, unsigned block) { return (unsigned)((n + block - 1) / block); }
 
-// Block size for a one-thread-per-item kernel: with few items (cfg 2 has 2^16) the grid is about one wave,
-// and the time is set by the SM that received the most blocks.  Pick the block size whose block count
+// ------------------------------------------------------------------------------------------------
+// Mixed-length batches (BASELINE config 5): longest-processing-time-first order.
+// A sponge is sequential per message, so with one thread per message the job cannot finish before
+// the longest message does.  Items are bucketed by block count (counting sort on the device) and
+// processed longest first; when the longest chain would dominate, the launch is limited to 1-3 warps
+// per scheduler (dynamic shared memory as an occupancy throttle) so that chain advances at full speed.
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t kLenBins = 1u << 16;
+
+__device__ __forceinline__ uint32_t len_bin(const uint64_t* off, uint64_t i, uint32_t stride_bytes) {
+  const uint64_t blocks = (off[i + 1] - off[i]) / stride_bytes;
+  return blocks < kLenBins - 1 ? (uint32_t)blocks : kLenBins - 1;
+}
+
+__global__ void len_hist_kernel(const uint64_t* __restrict__ off, uint64_t n, uint32_t stride_bytes, uint32_t* hist) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) atomicAdd(&hist[len_bin(off, i, stride_bytes)], 1u);
+}
+
+// hist[k] := number of items in bins > k (start of bin k in descending order); summary = {total blocks
+// (lo, hi), max bin, number of non-empty bins}
+__global__ void len_scan_kernel(uint32_t* hist, uint32_t* summary) {
+  __shared__ uint32_t part[1024];
+  __shared__ unsigned long long tot_s;
+  __shared__ uint32_t max_s, bins_s;
+  const uint32_t t = threadIdx.x;  // 1024 threads x 64 bins, thread 0 owns the HIGHEST bins
+  constexpr uint32_t PER = kLenBins / 1024;
+  if (t == 0) { tot_s = 0; max_s = 0; bins_s = 0; }
+  __syncthreads();
+  const uint32_t hi = kLenBins - 1 - t * PER;  // bins hi, hi-1, ..., hi-PER+1
+  uint32_t sum = 0, nb = 0, mx = 0;
+  unsigned long long tot = 0;
+  for (uint32_t k = 0; k < PER; k++) {
+    const uint32_t c = hist[hi - k];
+    sum += c;
+    if (c) { nb++; if (hi - k > mx) mx = hi - k; }
+    tot += (unsigned long long)c * (hi - k + 1);
+  }
+  part[t] = sum;
+  atomicAdd(&tot_s, tot);
+  atomicMax(&max_s, mx);
+  atomicAdd(&bins_s, nb);
+  __syncthreads();
+  // exclusive scan of part[] (simple Hillis-Steele on 1024 entries)
+  for (uint32_t d = 1; d < 1024; d <<= 1) {
+    uint32_t v = t >= d ? part[t - d] : 0;
+    __syncthreads();
+    part[t] += v;
+    __syncthreads();
+  }
+  uint32_t run = part[t] - sum;  // items in bins above this thread's range
+  for (uint32_t k = 0; k < PER; k++) {
+    const uint32_t c = hist[hi - k];
+    hist[hi - k] = run;
+    run += c;
+  }
+  if (t == 0) {
+    summary[0] = (uint32_t)tot_s;
+    summary[1] = (uint32_t)(tot_s >> 32);
+    summary[2] = max_s;
+    summary[3] = bins_s;
+  }
+}
+
+__global__ void len_scatter_kernel(const uint64_t* __restrict__ off, uint64_t n, uint32_t stride_bytes, uint32_t* cursor,
+                                   uint32_t* __restrict__ order) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) order[atomicAdd(&cursor[len_bin(off, i, stride_bytes)], 1u)] = (uint32_t)i;
+}
+
+struct LaunchPlan {
+  const uint32_t* order = nullptr;
+  int warps_per_smsp = 0;  // 0 = unthrottled
+};
+
+// builds the descending-length order for a ragged batch; decides the occupancy throttle
+static int plan_ragged(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t st, const uint64_t* d_off, uint64_t n,
+                       uint32_t stride_bytes, LaunchPlan* plan) {
+  *plan = LaunchPlan();
+  if (n < 2 || n > 0xffffffffull) return CAPY_OK;
+  int si = 0;  // scratch pair per internal stream (chunks on different streams overlap); callers' streams use pair 0
+  for (int k = 0; k < kNumStreams; k++)
+    if (dc.streams[k] == st) si = k;
+  uint32_t* hist = (uint32_t*)scratch_get(dc, 18 + 2 * si, (size_t)kLenBins * 4 + 64);
+  uint32_t* order = (uint32_t*)scratch_get(dc, 19 + 2 * si, (size_t)n * 4);
+  if (!hist || !order) return CAPY_ERR_OOM;
+  uint32_t* summary = hist + kLenBins;
+  CAPY_CUDA(ctx, cudaMemsetAsync(hist, 0, (size_t)kLenBins * 4 + 64, st));
+  len_hist_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_off, n, stride_bytes, hist);
+  len_scan_kernel<<<1, 1024, 0, st>>>(hist, summary);
+  ctx->launches += 2;
+  uint32_t h_sum[4];
+  CAPY_CUDA(ctx, cudaMemcpyAsync(h_sum, summary, sizeof h_sum, cudaMemcpyDeviceToHost, st));
+  CAPY_CUDA(ctx, cudaStreamSynchronize(st));
+  const uint64_t total_blocks = (uint64_t)h_sum[0] | ((uint64_t)h_sum[1] << 32);
+  const uint32_t max_blocks = h_sum[2] + 1, bins = h_sum[3];
+  if (bins <= 1) return CAPY_OK;  // uniform lengths: nothing to order
+  len_scatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_off, n, stride_bytes, hist, order);
+  ctx->launches++;
+  CAPY_CUDA(ctx, cudaGetLastError());
+  plan->order = order;
+  // time in units of one warp-permutation on one scheduler: all work spread over every scheduler vs the
+  // longest chain at w warps per scheduler
+  const double ideal = (double)total_blocks / (32.0 * 4.0 * dc.sm_count);
+  plan->warps_per_smsp = 0;
+  if ((double)max_blocks * 4.0 > 0.7 * ideal) {
+    plan->warps_per_smsp = 3;
+    if ((double)max_blocks * 3.0 > 0.7 * ideal) plan->warps_per_smsp = 2;
+    if ((double)max_blocks * 2.0 > 0.7 * ideal) plan->warps_per_smsp = 1;
+  }
+  return CAPY_OK;
+}
+
+template <int LANES>
+static int launch_sponge_t(capy_ctx* ctx, cudaStream_t stream, const SpongeJob& J, unsigned block, int warps_per_smsp) {
+  size_t smem = 0;
+  if (warps_per_smsp >= 1 && warps_per_smsp <= 3) {
+    // one 128-thread block = one warp per scheduler; W blocks per SM via the shared-memory footprint
+    block = 128;
+    smem = (size_t)(227 * 1024 / warps_per_smsp) - 1024;
+    CAPY_CUDA(ctx, cudaFuncSetAttribute(sponge_kernel<LANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+  }
+  sponge_kernel<LANES><<<grid_for(J.n, block), block, smem, stream>>>(J);
+  ctx->launches++;
+  CAPY_CUDA(ctx, cudaGetLastError());
+  return CAPY_OK;
+}
+
+// Block size for a one-thread-per-item kernel with few items: pick the block size whose block count
 // spreads most evenly over the SMs (ties go to the larger block).
 static unsigned pick_block(uint64_t n, int sm_count, int threads_per_sm) {
   unsigned best = 128;
@@ -121,7 +248,6 @@ static unsigned pick_block(uint64_t n, int sm_count, int threads_per_sm) {
     const uint64_t blocks = (n + bs - 1) / bs;
     const uint64_t slots = (uint64_t)sm_count * (threads_per_sm / bs);  // resident blocks per wave
     const uint64_t waves = (blocks + slots - 1) / slots;
-    // work of the busiest SM relative to a perfectly even spread
     const double per_sm = (double)blocks / sm_count;
     const double busiest = waves > 1 ? (double)waves * (threads_per_sm / bs) : (double)((blocks + sm_count - 1) / sm_count);
     const double eff = per_sm / busiest;
@@ -133,21 +259,19 @@ static unsigned pick_block(uint64_t n, int sm_count, int threads_per_sm) {
   return best;
 }
 
-static int launch_sponge(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t stream, int lanes, const SpongeJob& J) {
+static int launch_sponge(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t stream, int lanes, const SpongeJob& J,
+                         int warps_per_smsp = 0) {
   if (J.n == 0) return CAPY_OK;
-  const unsigned block = pick_block(J.n, dc.sm_count, 512), grid = grid_for(J.n, block);
+  const unsigned block = pick_block(J.n, dc.sm_count, 384);
   switch (lanes) {
-    case 9: sponge_kernel<9><<<grid, block, 0, stream>>>(J); break;
-    case 13: sponge_kernel<13><<<grid, block, 0, stream>>>(J); break;
-    case 17: sponge_kernel<17><<<grid, block, 0, stream>>>(J); break;
-    case 18: sponge_kernel<18><<<grid, block, 0, stream>>>(J); break;
-    case 19: sponge_kernel<19><<<grid, block, 0, stream>>>(J); break;
-    case 21: sponge_kernel<21><<<grid, block, 0, stream>>>(J); break;
+    case 9: return launch_sponge_t<9>(ctx, stream, J, block, warps_per_smsp);
+    case 13: return launch_sponge_t<13>(ctx, stream, J, block, warps_per_smsp);
+    case 17: return launch_sponge_t<17>(ctx, stream, J, block, warps_per_smsp);
+    case 18: return launch_sponge_t<18>(ctx, stream, J, block, warps_per_smsp);
+    case 19: return launch_sponge_t<19>(ctx, stream, J, block, warps_per_smsp);
+    case 21: return launch_sponge_t<21>(ctx, stream, J, block, warps_per_smsp);
     default: return CAPY_ERR_BAD_ARG;
   }
-  ctx->launches++;
-  CAPY_CUDA(ctx, cudaGetLastError());
-  return CAPY_OK;
 }
 
 static SpongeJob empty_job() {
@@ -158,7 +282,7 @@ static SpongeJob empty_job() {
 
 // ---- SHA3-d ------------------------------------------------------------------------------------
 static int launch_sha3(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t stream, int d, const uint8_t* data, const uint64_t* off,
-                       uint64_t msg_len, uint64_t stride, uint64_t n, uint8_t* out) {
+                       uint64_t msg_len, uint64_t stride, uint64_t n, uint8_t* out, uint32_t flags = 0) {
   if (!valid_secparam(d)) return CAPY_ERR_BAD_SECPARAM;
   if (n == 0) return CAPY_OK;
   const uint32_t rate = (1600 - sha3_capacity(d)) / 8;  // 144 / 136 / 104 / 72
@@ -188,7 +312,13 @@ static int launch_sha3(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t stream, int d,
   J.out_stride = J.out_bytes = (uint64_t)d / 8;
   J.sq_lanes = (1600 - d) / 64;  // Rate::from(&d), sponge.rs:27 (first d/8 bytes are all that is kept)
   J.n = n;
-  return launch_sponge(ctx, dc, stream, lanes, J);
+  LaunchPlan plan;
+  if (off && !(flags & CAPY_FLAG_NO_SORT)) {
+    int rc = plan_ragged(ctx, dc, stream, off, n, rate, &plan);
+    if (rc) return rc;
+  }
+  J.order = plan.order;
+  return launch_sponge(ctx, dc, stream, lanes, J, plan.warps_per_smsp);
 }
 
 // ---- cSHAKE / KMAC prefix -----------------------------------------------------------------------
@@ -282,7 +412,13 @@ static int launch_cshake(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t stream, int 
   J.out = out;
   J.out_stride = J.out_bytes = out_bits / 8;
   J.n = n;
-  return launch_sponge(ctx, dc, stream, (int)(bytepad_value(d) * 8 / 64), J);
+  LaunchPlan plan;
+  if (off) {
+    rc = plan_ragged(ctx, dc, stream, off, n, J.rate & ~7u, &plan);
+    if (rc) return rc;
+  }
+  J.order = plan.order;
+  return launch_sponge(ctx, dc, stream, (int)(bytepad_value(d) * 8 / 64), J, plan.warps_per_smsp);
 }
 
 int launch_kmac_xof(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t stream, const KmacDevArgs& a) {
@@ -310,7 +446,13 @@ int launch_kmac_xof(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t stream, const Kma
   J.out_stride = a.out_stride;
   J.out_bytes = a.out_bytes;
   J.n = a.n;
-  return launch_sponge(ctx, dc, stream, (int)(bytepad_value(a.d_bits) * 8 / 64), J);
+  LaunchPlan plan;
+  if (a.off && !a.no_sort) {
+    rc = plan_ragged(ctx, dc, stream, a.off, a.n, J.rate & ~7u, &plan);
+    if (rc) return rc;
+  }
+  J.order = plan.order;
+  return launch_sponge(ctx, dc, stream, (int)(bytepad_value(a.d_bits) * 8 / 64), J, plan.warps_per_smsp);
 }
 
 }  // namespace capy
@@ -323,11 +465,11 @@ extern "C" {
 // SHA3-d
 // =================================================================================================
 int capy_sha3_batch_dev(capy_ctx* ctx, int dev_index, void* stream, int d_bits, const uint8_t* d_data,
-                        const uint64_t* d_off, uint64_t n, uint8_t* d_digests, uint32_t) {
+                        const uint64_t* d_off, uint64_t n, uint8_t* d_digests, uint32_t flags) {
   if (!ctx || dev_index < 0 || dev_index >= (int)ctx->devs.size() || (n && (!d_data || !d_off || !d_digests)))
     return CAPY_ERR_BAD_ARG;
   DeviceGuard g(ctx->devs[dev_index].dev);
-  return launch_sha3(ctx, ctx->devs[dev_index], (cudaStream_t)stream, d_bits, d_data, d_off, 0, 0, n, d_digests);
+  return launch_sha3(ctx, ctx->devs[dev_index], (cudaStream_t)stream, d_bits, d_data, d_off, 0, 0, n, d_digests, flags);
 }
 
 int capy_sha3_batch_fixed_dev(capy_ctx* ctx, int dev_index, void* stream, int d_bits, const uint8_t* d_data,
@@ -339,7 +481,7 @@ int capy_sha3_batch_fixed_dev(capy_ctx* ctx, int dev_index, void* stream, int d_
 }
 
 int capy_sha3_batch(capy_ctx* ctx, int d_bits, const uint8_t* data, const uint64_t* off, uint64_t n, uint8_t* digests,
-                    uint32_t) {
+                    uint32_t flags) {
   if (!ctx || (n && (!data || !off || !digests))) return CAPY_ERR_BAD_ARG;
   if (!valid_secparam(d_bits)) return CAPY_ERR_BAD_SECPARAM;
   if (n == 0) return CAPY_OK;
@@ -347,7 +489,10 @@ int capy_sha3_batch(capy_ctx* ctx, int d_bits, const uint8_t* data, const uint64
   const size_t ob = (size_t)d_bits / 8;
   auto shards = split_items(off, 0, 0, n, ctx->devs.size(), 200);
   return for_each_device(ctx, shards, [&](DeviceCtx& dc, Range sh) -> int {
-    auto chunks = split_items(off, 0, sh.i0, sh.i1, chunk_count(off[sh.i1] - off[sh.i0], sh.i1 - sh.i0), 200);
+    const uint64_t bytes = off[sh.i1] - off[sh.i0], items = sh.i1 - sh.i0;
+    // long messages: few big chunks, so that the longest-first schedule sees the whole shard
+    const size_t nchunks = bytes / items > 8192 ? (size_t)std::max<uint64_t>(1, bytes >> 31) : chunk_count(bytes, items);
+    auto chunks = split_items(off, 0, sh.i0, sh.i1, nchunks, 200);
     for (size_t c = 0; c < chunks.size(); c++) {
       const int s = (int)(c % kNumStreams);
       cudaStream_t st = dc.streams[s];
@@ -357,7 +502,7 @@ int capy_sha3_batch(capy_ctx* ctx, int d_bits, const uint8_t* data, const uint64
       if (rc) return rc;
       uint8_t* d_out = (uint8_t*)scratch_get(dc, 3 * s + 2, (size_t)(ch.i1 - ch.i0) * ob);
       if (!d_out) return CAPY_ERR_OOM;
-      rc = launch_sha3(ctx, dc, st, d_bits, sp.d_base, sp.d_off, 0, 0, ch.i1 - ch.i0, d_out);
+      rc = launch_sha3(ctx, dc, st, d_bits, sp.d_base, sp.d_off, 0, 0, ch.i1 - ch.i0, d_out, flags);
       if (rc) return rc;
       CAPY_CUDA(ctx, cudaMemcpyAsync(digests + ch.i0 * ob, d_out, (size_t)(ch.i1 - ch.i0) * ob, cudaMemcpyDeviceToHost, st));
     }

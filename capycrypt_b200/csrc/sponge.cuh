@@ -15,6 +15,10 @@
 #pragma once
 #include "keccak.cuh"
 
+#ifndef CAPY_SPONGE_MINB
+#define CAPY_SPONGE_MINB 3
+#endif
+
 namespace capy {
 
 struct SpongeJob {
@@ -146,70 +150,124 @@ __device__ __forceinline__ void sponge_item(const SpongeJob& J, uint64_t i) {
   }
 
   // ---- absorb (sponge.rs:47-60) -------------------------------------------------------
+  // Blocks [fb0, fb1) lie wholly inside X: they are loaded straight from global memory, with the next
+  // block's loads issued BEFORE the current permutation (software prefetch: at one warp per scheduler --
+  // the long-message launch -- there is no other warp to hide the load latency).  The blocks before and
+  // after that range touch a segment boundary and are assembled lane by lane from the virtual stream.
   constexpr uint64_t STRIDE = 8ull * LANES;  // bytes consumed per block (168 for the 172 quirk)
-  for (uint64_t b = J.skip_blocks; b < nblocks; b++) {
+  uint64_t fb0 = (x0 + STRIDE - 1) / STRIDE, fb1 = x1 / STRIDE;
+  if (fb0 < J.skip_blocks) fb0 = J.skip_blocks;
+  if (fb1 > nblocks) fb1 = nblocks;
+  if (fb1 < fb0) fb1 = fb0;
+  if (fb0 > nblocks) fb0 = fb1 = nblocks;
+
+  auto slow_block = [&](uint64_t b) {
     const uint64_t s = b * STRIDE;
-    if (s >= x0 && s + STRIDE <= x1) {
-      const uint8_t* p = x + (s - x0);
-      if ((reinterpret_cast<uintptr_t>(p) & 7u) == 0) {
-        const uint2* q = reinterpret_cast<const uint2*>(p);
-#pragma unroll
-        for (int j = 0; j < LANES; j++) {
-          uint2 v = __ldg(q + j);
-          a[j].lo ^= v.x;
-          a[j].hi ^= v.y;
-        }
-      } else {
-        // unaligned message start: aligned 32-bit words + funnel shift by the byte phase
-        const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 3u) * 8u;
-        const uint32_t* q = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)3);
-        uint32_t w0 = __ldg(q);
-#pragma unroll
-        for (int j = 0; j < LANES; j++) {
-          uint32_t w1 = __ldg(q + 2 * j + 1);
-          // the third word is only needed (and only guaranteed readable) when sh != 0
-          uint32_t w2 = (sh != 0 || j + 1 < LANES) ? __ldg(q + 2 * j + 2) : 0u;
-          a[j].lo ^= __funnelshift_r(w0, w1, sh);
-          a[j].hi ^= __funnelshift_r(w1, w2, sh);
-          w0 = w2;
-        }
-      }
-    } else {
-      // boundary block: assemble lane by lane from the virtual stream
-      uint64_t blk[LANES];
+    uint64_t blk[LANES];
 #pragma unroll 1
-      for (int j = 0; j < LANES; j++) {
-        const uint64_t o = s + 8ull * j;
-        uint64_t v = 0;
-        if (o >= x0 && o + 8 <= x1) {
-          const uint8_t* p = x + (o - x0);
+    for (int j = 0; j < LANES; j++) {
+      const uint64_t o = s + 8ull * j;
+      uint64_t v = 0;
+      if (o >= x0 && o + 8 <= x1) {
+        const uint8_t* p = x + (o - x0);
 #pragma unroll
-          for (int k = 0; k < 8; k++) v |= (uint64_t)p[k] << (8 * k);
-        } else {
+        for (int k = 0; k < 8; k++) v |= (uint64_t)p[k] << (8 * k);
+      } else if (o < padded) {
 #pragma unroll 1
-          for (int k = 0; k < 8; k++) {
-            const uint64_t pos = o + k;
-            uint32_t byte;
-            if (pos < J.prefix_len) byte = J.prefix[pos];
-            else if (pos < x0) byte = key_block_byte(pos - J.prefix_len, key, klen, J.w, w_nb, k_nb);
-            else if (pos < x1) byte = x[pos - x0];
-            else if (pos < t1) byte = (trailer >> (8 * (uint32_t)(pos - x1))) & 0xFF;
-            else if (has_pad && pos == padded - 1) byte = 0x80;
-            else if (has_pad1 && pos == p1 - 1) byte = 0x80;
-            else byte = 0;
-            v |= (uint64_t)byte << (8 * k);
-          }
+        for (int k = 0; k < 8; k++) {
+          const uint64_t pos = o + k;
+          uint32_t byte;
+          if (pos < J.prefix_len) byte = J.prefix[pos];
+          else if (pos < x0) byte = key_block_byte(pos - J.prefix_len, key, klen, J.w, w_nb, k_nb);
+          else if (pos < x1) byte = x[pos - x0];
+          else if (pos < t1) byte = (trailer >> (8 * (uint32_t)(pos - x1))) & 0xFF;
+          else if (has_pad && pos == padded - 1) byte = 0x80;
+          else if (has_pad1 && pos == p1 - 1) byte = 0x80;
+          else byte = 0;
+          v |= (uint64_t)byte << (8 * k);
         }
-        blk[j] = v;
       }
+      blk[j] = v;
+    }
 #pragma unroll
-      for (int j = 0; j < LANES; j++) {
-        a[j].lo ^= (uint32_t)blk[j];
-        a[j].hi ^= (uint32_t)(blk[j] >> 32);
-      }
+    for (int j = 0; j < LANES; j++) {
+      a[j].lo ^= (uint32_t)blk[j];
+      a[j].hi ^= (uint32_t)(blk[j] >> 32);
     }
     keccak_f1600(a);
+  };
+
+#pragma unroll 1
+  for (uint64_t b = J.skip_blocks; b < fb0; b++) slow_block(b);
+
+  // The choice between the 8-byte-aligned and the byte-phase load path is made PER WARP: a per-thread
+  // branch here would put two separate permutation loops on the two sides of a divergent branch and
+  // the warp would run both back to back (measured 2.1x slower on ragged batches).
+  const uint8_t* p = x + (fb0 * STRIDE - x0);
+  const bool has_fast = fb0 < fb1;
+  const bool my_aligned = !has_fast || (reinterpret_cast<uintptr_t>(p) & 7u) == 0;
+#if defined(__CUDA_ARCH__)
+  const bool warp_aligned = __all_sync(__activemask(), my_aligned);
+#else
+  const bool warp_aligned = my_aligned;
+#endif
+  if (warp_aligned) {
+    const uint2* q = reinterpret_cast<const uint2*>(p);
+    uint2 cur[LANES];
+    if (has_fast) {
+#pragma unroll
+      for (int j = 0; j < LANES; j++) cur[j] = __ldg(q + j);
+    }
+#pragma unroll 1
+    for (uint64_t b = fb0; b < fb1; b++) {
+      q += LANES;
+      uint2 nxt[LANES];
+      if (b + 1 < fb1) {
+#pragma unroll
+        for (int j = 0; j < LANES; j++) nxt[j] = __ldg(q + j);
+      }
+#pragma unroll
+      for (int j = 0; j < LANES; j++) {
+        a[j].lo ^= cur[j].x;
+        a[j].hi ^= cur[j].y;
+      }
+      keccak_f1600(a);
+#pragma unroll
+      for (int j = 0; j < LANES; j++) cur[j] = nxt[j];
+    }
+  } else {
+    // any byte phase: aligned 32-bit words + funnel shift (sh == 0 for 4-byte aligned starts)
+    const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 3u) * 8u;
+    const uint32_t* q = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)3);
+    uint32_t cw[2 * LANES + 1];
+    if (has_fast) {
+#pragma unroll
+      for (int j = 0; j < 2 * LANES; j++) cw[j] = __ldg(q + j);
+      // the last word is only needed (and only guaranteed readable) when sh != 0
+      cw[2 * LANES] = sh != 0 ? __ldg(q + 2 * LANES) : 0u;
+    }
+#pragma unroll 1
+    for (uint64_t b = fb0; b < fb1; b++) {
+      q += 2 * LANES;
+      uint32_t nw[2 * LANES + 1];
+      if (b + 1 < fb1) {
+#pragma unroll
+        for (int j = 0; j < 2 * LANES; j++) nw[j] = __ldg(q + j);
+        nw[2 * LANES] = sh != 0 ? __ldg(q + 2 * LANES) : 0u;
+      }
+#pragma unroll
+      for (int j = 0; j < LANES; j++) {
+        a[j].lo ^= __funnelshift_r(cw[2 * j], cw[2 * j + 1], sh);
+        a[j].hi ^= __funnelshift_r(cw[2 * j + 1], cw[2 * j + 2], sh);
+      }
+      keccak_f1600(a);
+#pragma unroll
+      for (int j = 0; j < 2 * LANES + 1; j++) cw[j] = nw[j];
+    }
   }
+
+#pragma unroll 1
+  for (uint64_t b = fb1; b < nblocks; b++) slow_block(b);
 
   // ---- squeeze (sponge.rs:25-34, minus the dropped final permutation) -----------------------
   uint8_t* o;
@@ -242,7 +300,7 @@ __device__ __forceinline__ void sponge_item(const SpongeJob& J, uint64_t i) {
 }
 
 template <int LANES>
-__global__ void __launch_bounds__(128, 4) sponge_kernel(const SpongeJob J) {
+__global__ void __launch_bounds__(128, CAPY_SPONGE_MINB) sponge_kernel(const SpongeJob J) {
   const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= J.n) return;
   sponge_item<LANES>(J, J.order ? (uint64_t)J.order[t] : t);

@@ -48,6 +48,9 @@ extern "C" {
 
 /* flags */
 #define CAPY_FLAG_NONE 0u
+/* ragged batches are processed longest-message-first (device-side counting sort + one tiny D2H sync);
+ * this flag keeps the caller's order and makes the _dev call fully asynchronous */
+#define CAPY_FLAG_NO_SORT 1u
 
 typedef struct capy_ctx capy_ctx;
 

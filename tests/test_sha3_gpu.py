@@ -235,3 +235,38 @@ def test_device_pointer_api_and_shake_extra(engine, oracle):
         got = t_out.cpu().numpy().reshape(-1, 200)
         for m, g in zip(msgs, got):
             assert g.tobytes() == ref(m).digest(200)
+
+
+# ---- mixed-size batches (BASELINE config 5 shape): longest-first scheduling must not change any digest ----
+def test_mixed_size_sha3_512_vs_oracle(engine, oracle):
+    """Log-uniform lengths in [64 B, 1 MiB] incl. the quirk lengths len % 72 == 71 and len % 136 == 135;
+    every digest against the oracle; then the same batch with CAPY_FLAG_NO_SORT and permuted."""
+    import torch
+
+    rnd = np.random.default_rng(5)
+    lens = np.exp(rnd.uniform(np.log(64), np.log(1 << 20), size=600)).astype(np.int64)
+    lens[:8] = [71, 143, 135, 271, 72 * 1000 + 71, 136 * 500 + 135, 1 << 20, 64]
+    off = np.zeros(len(lens) + 1, np.uint64)
+    off[1:] = np.cumsum(lens)
+    data = rnd.integers(0, 256, size=int(off[-1]), dtype=np.uint8)
+    want = oracle.sha3_batch(data, off, 512, threads=0)
+    got = engine.sha3(data, off, 512)
+    assert np.array_equal(got, want), np.nonzero((got != want).any(axis=1))[0][:10]
+    t_data = torch.from_numpy(np.concatenate([data, np.zeros(8, np.uint8)])).cuda()
+    t_off = torch.from_numpy(off.astype(np.int64)).cuda()
+    t_out = torch.zeros(len(lens) * 64, dtype=torch.uint8, device="cuda")
+    engine._check(engine.lib.capy_sha3_batch_dev(engine._ctx, 0, engine._stream(), 512, t_data.data_ptr(), t_off.data_ptr(),
+                                                 len(lens), t_out.data_ptr(), 1))  # CAPY_FLAG_NO_SORT
+    torch.cuda.synchronize()
+    assert np.array_equal(t_out.cpu().numpy().reshape(-1, 64), want)
+
+
+def test_mixed_size_many_short_and_few_long(engine, oracle):
+    rnd = np.random.default_rng(6)
+    lens = np.concatenate([rnd.integers(0, 300, size=5000), rnd.integers(200000, 400000, size=5), [0, 0, 1]])
+    rnd.shuffle(lens)
+    off = np.zeros(len(lens) + 1, np.uint64)
+    off[1:] = np.cumsum(lens)
+    data = rnd.integers(0, 256, size=int(off[-1]), dtype=np.uint8)
+    for d in (256, 512):
+        assert np.array_equal(engine.sha3(data, off, d), oracle.sha3_batch(data, off, d, threads=0))
