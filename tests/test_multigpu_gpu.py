@@ -1,0 +1,46 @@
+"""GPU (needs >= 2 devices, skipped otherwise): one ctx spanning several GPUs shards host batches across them by
+contiguous ranges with no collective and returns the same bytes as a single-GPU ctx."""
+import numpy as np
+import pytest
+
+from capycrypt_b200 import Engine, pack
+
+pytestmark = pytest.mark.gpu
+
+
+def _ndev():
+    import torch
+
+    return torch.cuda.device_count()
+
+
+@pytest.mark.skipif("_ndev() < 2")
+def test_multi_device_ctx_matches_single(engine, oracle):
+    import torch
+
+    eng2 = Engine(devices=list(range(min(_ndev(), 8))))
+    assert eng2.device_count >= 2
+    rnd = np.random.default_rng(3)
+    lens = rnd.integers(0, 3000, size=20000)
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    data = rnd.integers(0, 256, size=int(off[-1]), dtype=np.uint8)
+    a = engine.sha3(data, off, 512)
+    b = eng2.sha3(data, off, 512)
+    assert np.array_equal(a, b)
+    idx = rnd.choice(len(lens), 500, replace=False)
+    msgs = [data[int(off[i]):int(off[i + 1])].tobytes() for i in idx]
+    d2, o2 = pack(msgs)
+    assert np.array_equal(a[idx], oracle.sha3_batch(d2, o2, 512, threads=0))
+    fixed = rnd.integers(0, 256, size=100000 * 64, dtype=np.uint8)
+    assert np.array_equal(engine.sha3_fixed(fixed, 64, 64, 100000, 256), eng2.sha3_fixed(fixed, 64, 64, 100000, 256))
+    sc = rnd.integers(0, 256, size=3000 * 56, dtype=np.uint8)
+    assert np.array_equal(engine.ed448_fixed_base(sc), eng2.ed448_fixed_base(sc))
+    pws, po = pack([bytes(rnd.integers(0, 256, size=16, dtype=np.uint8)) for _ in range(600)])
+    md, mo = pack([bytes(rnd.integers(0, 256, size=int(n), dtype=np.uint8)) for n in rnd.integers(0, 400, size=600)])
+    h1, z1 = engine.ed448_sign(pws, po, md, mo, 512)
+    h2, z2 = eng2.ed448_sign(pws, po, md, mo, 512)
+    assert np.array_equal(h1, h2) and np.array_equal(z1, z2)
+    pub = eng2.ed448_keygen(pws, po, 512)
+    rc, ok = eng2.ed448_verify(pub, md, mo, h2, z2, 512)
+    assert rc == 0 and ok.all()
+    eng2.close()
