@@ -87,7 +87,7 @@ inline int stage_packed(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t st, int slot_
   return CAPY_OK;
 }
 
-constexpr uint64_t kChunkBytes = 16ull << 20;
+constexpr uint64_t kChunkBytes = 8ull << 20;
 
 inline size_t chunk_count(uint64_t bytes, uint64_t items) {
   uint64_t c = (bytes + kChunkBytes - 1) / kChunkBytes;

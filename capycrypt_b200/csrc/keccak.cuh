@@ -2,7 +2,7 @@
 // registers as 50 x u32.  Replaces src/sha3/keccakf.rs:8-423 of the reference for batches.
 //
 // Instruction budget per round on the 32-bit datapath:
-//   theta parity 20 LOP3(xor3) + 10 SHF, theta-apply folded into rho input 50 LOP3,
+//   theta parity 20 LOP3(xor3) + 10 SHF (rot1 of the parities), theta-apply a ^ C[x-1] ^ rot1(C[x+1]) 50 LOP3,
 //   rho 48 SHF (funnel shifts on swapped halves), pi = register renaming, chi 50 LOP3
 //   (a ^ (~b & c) is one LOP3, imm 0xD2), iota 2 LOP3  ==> 122 LOP3 + 58 SHF = 180.
 // nvcc's default lowering of a 64-bit rotate is IMAD.SHL + SHF.R.U64 + SHF.R.U32.HI + LOP3,
@@ -39,42 +39,42 @@ __device__ __forceinline__ uint32_t lop_chi(uint32_t a, uint32_t b, uint32_t c) 
 template <int N>
 __device__ __forceinline__ Lane rotl64(Lane a) {
   Lane r;
-  if (N == 0) return a;
-  if (N == 32) {
+  if constexpr (N == 0) {
+    return a;
+  } else if constexpr (N == 32) {
     r.lo = a.hi;
     r.hi = a.lo;
-  } else if (N < 32) {
+    return r;
+  } else if constexpr (N < 32) {
     r.hi = __funnelshift_l(a.lo, a.hi, N);
     r.lo = __funnelshift_l(a.hi, a.lo, N);
+    return r;
   } else {
     r.hi = __funnelshift_l(a.hi, a.lo, N - 32);
     r.lo = __funnelshift_l(a.lo, a.hi, N - 32);
+    return r;
   }
-  return r;
 }
 
-// B[y][2x+3y] = rot(A[x][y] ^ D[x], rho[x][y]) for lane index x + 5y
-#define CAPY_RHO_PI(X, Y, R)                                            \
-  {                                                                     \
-    Lane t;                                                             \
-    t.lo = a[(X) + 5 * (Y)].lo ^ d[(X)].lo;                             \
-    t.hi = a[(X) + 5 * (Y)].hi ^ d[(X)].hi;                             \
-    b[(Y) + 5 * ((2 * (X) + 3 * (Y)) % 5)] = rotl64<(R)>(t);            \
+// B[y][2x+3y] = rot(A[x][y] ^ C[x-1] ^ rot1(C[x+1]), rho[x][y]) for lane index x + 5y.  D[x] is never
+// formed: the theta "apply" is a single 3-input XOR per half (this is what makes it 122 LOP3 per round).
+#define CAPY_RHO_PI(X, Y, R)                                                                  \
+  {                                                                                           \
+    Lane t;                                                                                   \
+    t.lo = lop_xor3(a[(X) + 5 * (Y)].lo, c[((X) + 4) % 5].lo, r1[((X) + 1) % 5].lo);          \
+    t.hi = lop_xor3(a[(X) + 5 * (Y)].hi, c[((X) + 4) % 5].hi, r1[((X) + 1) % 5].hi);          \
+    b[(Y) + 5 * ((2 * (X) + 3 * (Y)) % 5)] = rotl64<(R)>(t);                                  \
   }
 
 __device__ __forceinline__ void keccak_round(Lane (&a)[25], uint2 rc) {
-  Lane c[5], d[5], b[25];
+  Lane c[5], r1[5], b[25];
 #pragma unroll
   for (int x = 0; x < 5; x++) {
     c[x].lo = lop_xor3(lop_xor3(a[x].lo, a[x + 5].lo, a[x + 10].lo), a[x + 15].lo, a[x + 20].lo);
     c[x].hi = lop_xor3(lop_xor3(a[x].hi, a[x + 5].hi, a[x + 10].hi), a[x + 15].hi, a[x + 20].hi);
   }
 #pragma unroll
-  for (int x = 0; x < 5; x++) {
-    Lane t = rotl64<1>(c[(x + 1) % 5]);
-    d[x].lo = c[(x + 4) % 5].lo ^ t.lo;
-    d[x].hi = c[(x + 4) % 5].hi ^ t.hi;
-  }
+  for (int x = 0; x < 5; x++) r1[x] = rotl64<1>(c[x]);
   CAPY_RHO_PI(0, 0, 0)  CAPY_RHO_PI(1, 0, 1)  CAPY_RHO_PI(2, 0, 62) CAPY_RHO_PI(3, 0, 28) CAPY_RHO_PI(4, 0, 27)
   CAPY_RHO_PI(0, 1, 36) CAPY_RHO_PI(1, 1, 44) CAPY_RHO_PI(2, 1, 6)  CAPY_RHO_PI(3, 1, 55) CAPY_RHO_PI(4, 1, 20)
   CAPY_RHO_PI(0, 2, 3)  CAPY_RHO_PI(1, 2, 10) CAPY_RHO_PI(2, 2, 43) CAPY_RHO_PI(3, 2, 25) CAPY_RHO_PI(4, 2, 39)

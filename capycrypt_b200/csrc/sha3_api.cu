@@ -89,6 +89,45 @@ __global__ void __launch_bounds__(128)
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// single-block SHA3-d of messages of exactly 8 * MSG_LANES bytes (MSG_LANES < LANES), 16-byte aligned
+// rows: the BASELINE cfg-1 shape (2^20 x 64 B).  Everything about the block layout is a compile-time
+// constant: message lanes come in with 128-bit loads, the suffix / 0x80 lanes are immediates, round 0 is
+// peeled so that the zero lanes fold away, and the remaining 23 rounds run two per loop iteration.
+// ------------------------------------------------------------------------------------------------
+template <int LANES, int MSG_LANES>
+__global__ void __launch_bounds__(128)
+    sha3_short_kernel(const uint4* __restrict__ data, uint64_t stride16, uint32_t suffix, uint4* __restrict__ out,
+                      uint32_t out_bytes, uint64_t n) {
+  static_assert(MSG_LANES % 2 == 0 && MSG_LANES < LANES, "whole 16-byte loads, one block");
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint4* q = data + i * stride16;
+  Lane a[25];
+  state_zero(a);
+#pragma unroll
+  for (int j = 0; j < MSG_LANES / 2; j++) {
+    const uint4 v = __ldg(q + j);
+    a[2 * j].lo = v.x;
+    a[2 * j].hi = v.y;
+    a[2 * j + 1].lo = v.z;
+    a[2 * j + 1].hi = v.w;
+  }
+  a[MSG_LANES].lo = suffix;  // 0x06 (0x86 can only occur for 135-byte messages, which are not 8-byte multiples)
+  a[LANES - 1].hi ^= 0x80000000u;  // 8 * MSG_LANES + 1 < rate always holds here: zeros then 0x80 (sponge.rs:89-95)
+  keccak_round(a, KECCAK_RC[0]);
+#pragma unroll 1
+  for (int r = 1; r < 23; r += 2) {
+    keccak_round(a, KECCAK_RC[r]);
+    keccak_round(a, KECCAK_RC[r + 1]);
+  }
+  keccak_round(a, KECCAK_RC[23]);
+  uint4* o = out + i * (uint64_t)(out_bytes / 16);
+#pragma unroll
+  for (int j = 0; j < 4; j++)
+    if (16u * j < out_bytes) o[j] = make_uint4(a[2 * j].lo, a[2 * j].hi, a[2 * j + 1].lo, a[2 * j + 1].hi);
+}
+
 // one thread absorbs the whole-block part of a constant prefix into a cached state
 template <int LANES>
 __global__ void prefix_state_kernel(const uint8_t* prefix, uint32_t nblocks, uint64_t* state) {
@@ -287,6 +326,20 @@ static int launch_sha3(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t stream, int d,
   if (n == 0) return CAPY_OK;
   const uint32_t rate = (1600 - sha3_capacity(d)) / 8;  // 144 / 136 / 104 / 72
   const int lanes = (int)rate / 8;
+  if (!off && (reinterpret_cast<uintptr_t>(data) & 15u) == 0 && (reinterpret_cast<uintptr_t>(out) & 15u) == 0 &&
+      (stride & 15u) == 0 && (d == 256 || d == 512) && (msg_len == 64 || msg_len == 32)) {
+    // compile-time block layout (cfg 1)
+    const unsigned block = 128, grid = grid_for(n, block);
+    const uint4* dq = reinterpret_cast<const uint4*>(data);
+    uint4* oq = reinterpret_cast<uint4*>(out);
+    if (d == 256 && msg_len == 64) sha3_short_kernel<17, 8><<<grid, block, 0, stream>>>(dq, stride / 16, 0x06u, oq, 32, n);
+    else if (d == 256) sha3_short_kernel<17, 4><<<grid, block, 0, stream>>>(dq, stride / 16, 0x06u, oq, 32, n);
+    else if (msg_len == 64) sha3_short_kernel<9, 8><<<grid, block, 0, stream>>>(dq, stride / 16, 0x06u, oq, 64, n);
+    else sha3_short_kernel<9, 4><<<grid, block, 0, stream>>>(dq, stride / 16, 0x06u, oq, 64, n);
+    ctx->launches++;
+    CAPY_CUDA(ctx, cudaGetLastError());
+    return CAPY_OK;
+  }
   if (!off && (reinterpret_cast<uintptr_t>(data) & 7u) == 0 && (stride & 7u) == 0) {
     const uint32_t suffix = (msg_len % 136u == 135u) ? 0x86u : 0x06u;  // shake_functions.rs:25-29 (Q2)
     const unsigned block = 128, grid = grid_for(n, block);

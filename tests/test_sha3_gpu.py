@@ -106,7 +106,7 @@ def test_sha3_ragged_long(engine, oracle, d):
 
 
 @pytest.mark.parametrize("d", DS)
-@pytest.mark.parametrize("msg_len,stride", [(64, 64), (0, 8), (1, 8), (63, 64), (71, 72), (135, 136), (136, 136),
+@pytest.mark.parametrize("msg_len,stride", [(64, 64), (32, 32), (32, 48), (64, 80), (0, 8), (1, 8), (63, 64), (71, 72), (135, 136), (136, 136),
                                              (143, 144), (200, 200), (1000, 1000), (4096, 4096), (100, 128),
                                              (64, 65), (33, 33)])
 def test_sha3_fixed(engine, oracle, d, msg_len, stride):
