@@ -8,7 +8,8 @@
 // exceptional points), so every input -- identity, small-order points, P + P -- takes the same path.
 //
 // Scalar multiplication is a fixed-window ladder on signed radix-16 digits:
-//   fixed base   112 windows x 8 affine entries (j+1) * 16^i * G  -> 112 mixed additions, no doubling
+//   fixed base   on the 4-isogenous twisted curve: 90 windows x 16 Niels entries (j+1) * 32^i * phi(G)
+//                -> 90 mixed additions of 7 M, no doubling, dual isogeny back to E at the end
 //   variable     per-item table 1P..8P, 113 windows x (4 doublings + 1 addition)
 // Table entries are chosen by a constant-time scan (every entry is read, the wanted one is kept
 // with a mask) unless the caller states that the scalar is public (verify).
@@ -22,9 +23,6 @@ constexpr uint32_t EDW_D_ABS = 39081u;  // d = -39081
 
 struct PtExt {  // extended projective, all coordinates tight
   Fe X, Y, Z, T;
-};
-struct PtAffN {  // affine table entry: x, y, td = d*x*y
-  Fe x, y, td;
 };
 struct PtCached {  // projective table entry: X, Y, Z, Td = d*T
   Fe X, Y, Z, Td;
@@ -62,21 +60,6 @@ CAPY_HD void add_tail(PtExt& r, const Fe& A, const Fe& B, const Fe& C, const Fe&
   fe_mul(r.Y, G, H);    // 2 x 3
   fe_mul(r.Z, F, G);    // 3 x 2
   if (WANT_T) fe_mul(r.T, E, H);  // 1 x 3
-}
-
-// r = p + q, q an affine table entry (Z2 = 1): 8 M
-template <bool WANT_T>
-CAPY_HD void pt_madd(PtExt& r, const PtExt& p, const PtAffN& q) {
-  Fe A, B, C, E0, s1, s2;
-  fe_mul(A, p.X, q.x);
-  fe_mul(B, p.Y, q.y);
-  fe_mul(C, p.T, q.td);
-  fe_add(s1, p.X, p.Y);  // alpha 2
-  fe_add(s2, q.x, q.y);  // alpha 2
-  fe_mul(E0, s1, s2);    // 2 x 2
-  Fe D;
-  fe_copy(D, p.Z);
-  add_tail<WANT_T>(r, A, B, C, D, E0);
 }
 
 // r = p + q, q a projective table entry: 9 M
@@ -155,14 +138,7 @@ CAPY_HD void sc_recode_radix16(int8_t* dig /*[113]*/, const Sc& k) {
   dig[112] = (int8_t)carry;
 }
 
-// constant-time conditional negation of an affine entry: -(x, y) = (-x, y), td -> -td
-CAPY_HD void ptaff_cneg(PtAffN& e, uint32_t neg_mask) {
-  Fe nx, ntd;
-  fe_neg(nx, e.x);
-  fe_neg(ntd, e.td);
-  fe_cmov(e.x, nx, neg_mask);
-  fe_cmov(e.td, ntd, neg_mask);
-}
+// constant-time conditional negation of a cached entry: -(X:Y:Z:T) = (-X:Y:Z:-T)
 CAPY_HD void ptcached_cneg(PtCached& e, uint32_t neg_mask) {
   Fe nx, ntd;
   fe_neg(nx, e.X);
@@ -171,11 +147,21 @@ CAPY_HD void ptcached_cneg(PtCached& e, uint32_t neg_mask) {
   fe_cmov(e.Td, ntd, neg_mask);
 }
 
-// ---- fixed-base comb ---------------------------------------------------------------------------
-// table layout: entry (i, j) = (j+1) * 16^i * G as 48 u32 words (x | y | td, 16 tight limbs each)
-constexpr int FB_WINDOWS = 112;
-constexpr int FB_ENTRIES = 8;
-constexpr int FB_ENTRY_WORDS = 48;
+// ---- fixed-base comb on the 4-isogenous twisted curve ------------------------------------------------
+// [k]G is computed as  phi^([k / 4 mod r] * phi(G))  where phi: E -> E' is the 4-isogeny onto the twisted
+// Edwards curve E': -x^2 + y^2 = 1 + (d - 1) x^2 y^2 and phi^ its dual (phi^ o phi = [4]; G has odd order r,
+// so this is exact).  On E' (a = -1) a mixed addition with a precomputed Niels entry (y - x, y + x, 2 d' x y)
+// costs 7 M instead of 8 M on E.  Signed radix-32 digits: 90 windows x 16 entries = 270 KB table, 90 mixed
+// additions and no doubling per scalar multiplication.
+constexpr int FB_WBITS = 5;
+constexpr int FB_WINDOWS = 90;
+constexpr int FB_ENTRIES = 16;
+constexpr int FB_ENTRY_WORDS = 48;  // ymx | ypx | td2, 16 canonical limbs each
+constexpr uint32_t EDW_2D_TW_ABS = 2u * 39082u;  // 2 d' = -78164
+
+struct PtNiels {  // affine point of E' as (y - x, y + x, 2 d' x y)
+  Fe ymx, ypx, td2;
+};
 
 #if defined(__CUDA_ARCH__)
 #define CAPY_LD128(p) __ldg(reinterpret_cast<const uint4*>(p))
@@ -183,15 +169,39 @@ constexpr int FB_ENTRY_WORDS = 48;
 #define CAPY_LD128(p) (*reinterpret_cast<const uint4*>(p))
 #endif
 
-// e = |dgt| * 16^i * G (identity representation x = 0, y = 1, td = 0 when dgt == 0), sign applied
-CAPY_HD void fb_lookup(PtAffN& e, const uint32_t* __restrict__ table, int i, int dgt, bool CONSTANT_TIME) {
+// r = p + q on E' (a = -1), q affine Niels: 7 M (add-2008-hwcd-3 with Z2 = 1)
+template <bool WANT_T>
+CAPY_HD void pt_madd_tw(PtExt& r, const PtExt& p, const PtNiels& q) {
+  Fe A, B, C, D, E, F, G, H, t0, t1;
+  fe_sub(t0, p.Y, p.X);      // alpha 3
+  fe_add(t1, p.Y, p.X);      // alpha 2
+  fe_mul(A, t0, q.ymx);      // 3 x 1
+  fe_mul(B, t1, q.ypx);      // 2 x 1
+  fe_mul(C, p.T, q.td2);     // 1 x 2 (td2 may be an unreduced negation)
+  fe_add(D, p.Z, p.Z);       // alpha 2
+  fe_sub(E, B, A);           // alpha 3
+  fe_add(H, B, A);           // alpha 2
+  fe_sub(F, D, C);           // alpha 4
+  fe_weak(F);                // tight
+  fe_add(G, D, C);           // alpha 3
+  fe_mul(r.X, E, F);         // 3 x 1
+  fe_mul(r.Y, G, H);         // 3 x 2
+  fe_mul(r.Z, F, G);         // 1 x 3
+  if (WANT_T) fe_mul(r.T, E, H);  // 3 x 2
+}
+
+// e = |dgt| * 32^i * phi(G) with the sign applied; dgt == 0 gives the identity (1, 1, 0).
+// `row` = the 16 entries of window i.  STAGED: the row sits in shared memory (plain loads, broadcast);
+// otherwise it is read from global memory through the read-only path.
+template <bool STAGED>
+CAPY_HD void fb_lookup_row(PtNiels& e, const uint32_t* __restrict__ row, int dgt, bool CONSTANT_TIME) {
   const uint32_t neg = dgt < 0 ? 0xffffffffu : 0u;
-  const uint32_t mag = (uint32_t)(dgt < 0 ? -dgt : dgt);  // 0..8
+  const uint32_t mag = (uint32_t)(dgt < 0 ? -dgt : dgt);  // 0..16
   uint32_t w[FB_ENTRY_WORDS];
 #pragma unroll
   for (int k = 0; k < FB_ENTRY_WORDS; k++) w[k] = 0;
-  w[16] = 1;  // y = 1
-  const uint32_t* row = table + (size_t)i * FB_ENTRIES * FB_ENTRY_WORDS;
+  w[0] = 1;   // y - x = 1
+  w[16] = 1;  // y + x = 1
   if (CONSTANT_TIME) {
 #pragma unroll 1
     for (uint32_t j = 1; j <= FB_ENTRIES; j++) {
@@ -199,7 +209,7 @@ CAPY_HD void fb_lookup(PtAffN& e, const uint32_t* __restrict__ table, int i, int
       const uint32_t* ent = row + (j - 1) * FB_ENTRY_WORDS;
 #pragma unroll
       for (int k = 0; k < FB_ENTRY_WORDS; k += 4) {
-        const uint4 v = CAPY_LD128(ent + k);
+        const uint4 v = STAGED ? *reinterpret_cast<const uint4*>(ent + k) : CAPY_LD128(ent + k);
         w[k + 0] = (v.x & m) | (w[k + 0] & ~m);
         w[k + 1] = (v.y & m) | (w[k + 1] & ~m);
         w[k + 2] = (v.z & m) | (w[k + 2] & ~m);
@@ -210,35 +220,71 @@ CAPY_HD void fb_lookup(PtAffN& e, const uint32_t* __restrict__ table, int i, int
     const uint32_t* ent = row + (mag - 1) * FB_ENTRY_WORDS;
 #pragma unroll
     for (int k = 0; k < FB_ENTRY_WORDS; k += 4) {
-      const uint4 v = CAPY_LD128(ent + k);
+      const uint4 v = STAGED ? *reinterpret_cast<const uint4*>(ent + k) : CAPY_LD128(ent + k);
       w[k + 0] = v.x;
       w[k + 1] = v.y;
       w[k + 2] = v.z;
       w[k + 3] = v.w;
     }
   }
+  // -(x, y) = (-x, y): swap (y - x) <-> (y + x), negate 2 d' x y (left unreduced: 2p - td2, alpha 2)
 #pragma unroll
   for (int k = 0; k < 16; k++) {
-    e.x.v[k] = w[k];
-    e.y.v[k] = w[16 + k];
-    e.td.v[k] = w[32 + k];
+    const uint32_t t = (w[k] ^ w[16 + k]) & neg;
+    e.ymx.v[k] = w[k] ^ t;
+    e.ypx.v[k] = w[16 + k] ^ t;
+    const uint32_t ntd = (k == 8 ? 2u * (M28 - 1u) : 2u * M28) - w[32 + k];
+    e.td2.v[k] = (ntd & neg) | (w[32 + k] & ~neg);
   }
-  ptaff_cneg(e, neg);
 }
 
-// r = [k]G for k in [0, r) via the comb table
+// signed radix-32 digit i of kq (with the running carry of the recoding)
+CAPY_HD int fb_digit(const Sc& kq, int i, uint32_t& carry) {
+  const int bit = FB_WBITS * i, q = bit >> 5, sh = bit & 31;
+  uint32_t v = kq.w[q] >> sh;
+  if (sh > 32 - FB_WBITS && q + 1 < 14) v |= kq.w[q + 1] << (32 - sh);
+  const uint32_t win = (v & ((1u << FB_WBITS) - 1u)) + carry;
+  carry = win >= (1u << (FB_WBITS - 1)) ? 1u : 0u;
+  return (int)win - (int)(carry << FB_WBITS);
+}
+
+// dual isogeny phi^: E' -> E on projective coordinates, result extended on E:
+//   x = 2XY / (Y^2 + X^2),  y = (Y^2 - X^2) / (2Z^2 - Y^2 + X^2)
+CAPY_HD void pt_dual_isogeny(PtExt& r, const PtExt& p) {
+  Fe A, B, ZZ, XY, xn, xd, yn, yd;
+  fe_sqr(A, p.X);
+  fe_sqr(B, p.Y);
+  fe_sqr(ZZ, p.Z);
+  fe_mul(XY, p.X, p.Y);
+  fe_add(xn, XY, XY);    // alpha 2
+  fe_add(xd, B, A);      // alpha 2
+  fe_sub(yn, B, A);      // alpha 3
+  fe_add(yd, ZZ, ZZ);    // alpha 2
+  fe_sub4(yd, yd, yn);   // alpha 6
+  fe_weak(yd);           // tight
+  fe_mul(r.X, xn, yd);   // 2 x 1
+  fe_mul(r.Y, yn, xd);   // 3 x 2
+  fe_mul(r.Z, xd, yd);   // 2 x 1
+  fe_mul(r.T, xn, yn);   // 2 x 3
+}
+
+// r = [k]G (extended, on E) for k in [0, r) via the comb table of phi(G) read from global memory
+// (the CUDA kernel in ed448_fixed.cu runs the same loop with the table rows staged through shared memory)
 CAPY_HD void pt_fixed_base_mul(PtExt& r, const Sc& k, const uint32_t* __restrict__ table, bool CONSTANT_TIME) {
-  pt_identity(r);
+  const Sc inv4 = {CAPY_INV4_LIMBS};
+  Sc kq;
+  sc_mul_mod(kq, k, inv4);  // k / 4 mod r
+  PtExt acc;
+  pt_identity(acc);  // (0, 1) is the identity of E' too
   uint32_t carry = 0;
 #pragma unroll 1
   for (int i = 0; i < FB_WINDOWS; i++) {
-    uint32_t nib = ((k.w[i >> 3] >> (4 * (i & 7))) & 15u) + carry;
-    carry = nib >= 8u ? 1u : 0u;
-    const int dgt = (int)nib - (int)(carry << 4);
-    PtAffN e;
-    fb_lookup(e, table, i, dgt, CONSTANT_TIME);
-    pt_madd<true>(r, r, e);
+    const int dgt = fb_digit(kq, i, carry);
+    PtNiels e;
+    fb_lookup_row<false>(e, table + (size_t)i * FB_ENTRIES * FB_ENTRY_WORDS, dgt, CONSTANT_TIME);
+    pt_madd_tw<true>(acc, acc, e);
   }
+  pt_dual_isogeny(r, acc);
 }
 
 // ---- variable base ------------------------------------------------------------------------------
@@ -323,31 +369,59 @@ CAPY_HD void pt_generator(PtExt& g) {
   fe_mul(g.T, g.X, g.Y);
 }
 
-// writes the 8 entries of window i: (j+1) * 16^i * G, affine, canonical limbs
-CAPY_HD void fb_build_window(uint32_t* row /*[8 * 48]*/, int i) {
+// writes the 16 entries of window i: (j+1) * 32^i * phi(G) as canonical Niels triples.  The multiples are
+// formed on E with the complete formulas, taken to affine, then pushed through the isogeny
+//   phi(x, y) = ( 2xy / (y^2 - x^2),  (y^2 + x^2) / (2 - y^2 - x^2) )     (a homomorphism E -> E')
+CAPY_HD void fb_build_window(uint32_t* row /*[16 * 48]*/, int i) {
   PtExt base;
   pt_generator(base);
 #pragma unroll 1
-  for (int k = 0; k < 4 * i; k++) pt_double<true>(base, base);
+  for (int k = 0; k < FB_WBITS * i; k++) pt_double<true>(base, base);
   PtCached cb;
   pt_to_cached(cb, base);
   PtExt acc = base;
 #pragma unroll 1
   for (int j = 0; j < FB_ENTRIES; j++) {
     if (j > 0) pt_add_cached<true>(acc, acc, cb);
-    Fe zi, x, y, td;
+    Fe zi, x, y, x2, y2, u, v, w, t, xt, yt, two;
     fe_inv(zi, acc.Z);
-    fe_mul(x, acc.X, zi);
-    fe_mul(y, acc.Y, zi);
-    fe_mul(td, x, y);
-    fe_mul_d(td, td);
-    fe_canon(x);
-    fe_canon(y);
+    fe_mul_call(&x, &acc.X, &zi);
+    fe_mul_call(&y, &acc.Y, &zi);
+    fe_sqr_call(&x2, &x);
+    fe_sqr_call(&y2, &y);
+    fe_sub(u, y2, x2);       // y^2 - x^2, alpha 3
+    fe_weak(u);
+    fe_add(t, y2, x2);       // y^2 + x^2, alpha 2
+    fe_zero(two);
+    two.v[0] = 2;
+    fe_weak(t);
+    fe_sub(v, two, t);       // 2 - y^2 - x^2
+    fe_weak(v);
+    fe_mul_call(&w, &u, &v);
+    fe_inv(w, w);            // 1 / (u v)
+    fe_mul_call(&xt, &x, &y);
+    fe_add(xt, xt, xt);      // 2xy, alpha 2
+    fe_weak(xt);
+    fe_mul_call(&xt, &xt, &v);
+    fe_mul_call(&xt, &xt, &w);  // x' = 2xy / u
+    fe_mul_call(&yt, &t, &u);
+    fe_mul_call(&yt, &yt, &w);  // y' = (y^2 + x^2) / v
+    Fe ymx, ypx, td;
+    fe_sub(ymx, yt, xt);
+    fe_add(ypx, yt, xt);
+    fe_mul_call(&td, &xt, &yt);
+    uint64_t R[16];
+    for (int k = 0; k < 16; k++) R[k] = (uint64_t)td.v[k] * EDW_2D_TW_ABS;
+    Fe td_abs;
+    fe_carry_wide(td_abs, R);
+    fe_neg(td, td_abs);      // 2 d' x' y' with d' = -39082
+    fe_canon(ymx);
+    fe_canon(ypx);
     fe_canon(td);
     uint32_t* e = row + j * FB_ENTRY_WORDS;
     for (int k = 0; k < 16; k++) {
-      e[k] = x.v[k];
-      e[16 + k] = y.v[k];
+      e[k] = ymx.v[k];
+      e[16 + k] = ypx.v[k];
       e[32 + k] = td.v[k];
     }
   }

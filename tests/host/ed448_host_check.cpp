@@ -91,7 +91,7 @@ int host_var_base(const uint8_t* k_be, const uint8_t* pt_xy, int constant_time, 
   pt_out(out_xy, r);
   return 0;
 }
-void host_table_entry(int i, int j, uint8_t* out_xy_td /*168*/) {
+void host_table_entry(int i, int j, uint8_t* out_xy_td /*168: ymx | ypx | td2*/) {
   const uint32_t* e = table() + ((size_t)i * FB_ENTRIES + j) * FB_ENTRY_WORDS;
   Fe x, y, td;
   for (int k = 0; k < 16; k++) { x.v[k] = e[k]; y.v[k] = e[16 + k]; td.v[k] = e[32 + k]; }

@@ -72,14 +72,24 @@ def test_scalar_ops(host):
         assert _sc(host, 3, a) == a % R
 
 
+def _phi(pt):
+    """4-isogeny E -> E' (twisted, a = -1, d' = d - 1): (2xy / (y^2 - x^2), (y^2 + x^2) / (2 - y^2 - x^2))."""
+    x, y = pt
+    return (2 * x * y * E.inv((y * y - x * x) % P) % P, (y * y + x * x) * E.inv((2 - y * y - x * x) % P) % P)
+
+
 def test_comb_table_entries(host):
+    """Entry (i, j) of the fixed-base table is (j+1) * 32^i * phi(G) as (y - x, y + x, 2 d' x y), d' = -39082."""
     o = (C.c_uint8 * 168)()
-    for i, j in [(0, 0), (0, 7), (1, 0), (5, 3), (60, 4), (111, 0), (111, 7)]:
+    d_tw = (E.D - 1) % P
+    for i, j in [(0, 0), (0, 15), (1, 0), (5, 3), (60, 4), (89, 0), (89, 15)]:
         host.host_table_entry(i, j, o)
         b = bytes(o)
-        pt = E.scalar_mult((j + 1) * 16**i, E.GENERATOR)
-        assert b[:112] == E.point_to_bytes(pt)
-        assert int.from_bytes(b[112:], "little") == E.D * pt[0] * pt[1] % P
+        x, y = _phi(E.scalar_mult((j + 1) * 32**i, E.GENERATOR))
+        assert (-x * x + y * y - 1 - d_tw * x * x * y * y) % P == 0
+        assert int.from_bytes(b[:56], "little") == (y - x) % P
+        assert int.from_bytes(b[56:112], "little") == (y + x) % P
+        assert int.from_bytes(b[112:], "little") == 2 * d_tw * x * y % P
 
 
 SCALARS = [0, 1, 2, 7, 8, 9, 15, 16, R - 1, R, R + 1, 2**446 - 1, 2**448 - 1, int("8" * 112, 16), int("7" * 112, 16),
