@@ -292,7 +292,7 @@ def main():
            "ms_per_step": e2e_s / k_e2e * 1e3,
            "api": "capy_sha3_batch_fixed (host buffers from capy_host_alloc, chunked H2D/kernel/D2H on 3 streams)"}
 
-    # ---- roofline of the dominant kernel (sha3_uniform_kernel<17>: one launch per step) ----
+    # ---- roofline of the dominant kernel (sha3_short_kernel<17, 8>: one launch per step) ----
     ops = N_MSGS * OPS_PER_PERM
     achieved = ops / (ms_per_step * 1e-3) * (1 if world == 1 else 1)  # per GPU
     hbm_bytes = N_MSGS * (MSG_LEN + DIGEST)
@@ -303,11 +303,11 @@ def main():
         hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("sha3_uniform_kernel<17>")
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("sha3_short_kernel<17, 8>")
     except Exception:
         pass
     roofline = {
-        "bound": "int_alu", "kernel": "sha3_uniform_kernel<17>", "achieved": achieved / 1e12, "peak": peaks["lop3"] / 1e12,
+        "bound": "int_alu", "kernel": "sha3_short_kernel<17, 8>", "achieved": achieved / 1e12, "peak": peaks["lop3"] / 1e12,
         "unit": "Tint32op/s", "frac": achieved / peaks["lop3"], "traffic": traffic,
         "peak_source": peaks.get("source", "profiles/r01_peaks_int_pipes.json"),
         "algorithmic": f"{OPS_PER_PERM} int32 LOP3/SHF per Keccak-f[1600] x 1 permutation x {N_MSGS} messages per launch",
