@@ -18,6 +18,8 @@ ERR_CUDA = -3
 ERR_BAD_POINT = -4
 ERR_NO_DEVICE = -5
 ERR_OOM = -6
+AE_SHA3 = 0
+AE_KEM = 1
 
 u8p = C.c_void_p  # raw addresses (host numpy buffers or device pointers)
 u64p = C.c_void_p
@@ -58,6 +60,15 @@ SIGNATURES = {
     "capy_ed448_verify_batch": (i32, [vp, i32, u8p, u8p, u64p, u8p, u8p, u64, u8p]),
     "capy_ed448_verify_batch_dev": (i32, [vp, i32, vp, i32, u8p, u8p, u64p, u8p, u8p, u64, u8p, vp]),
     "capy_ed448_ecdh_batch": (i32, [vp, u8p, u8p, u64, u8p, u8p]),
+    "capy_sponge_encrypt_batch": (i32, [vp, i32, i32, u8p, u64p, u8p, u64, u8p, u64p, u64, u8p, u8p]),
+    "capy_sponge_decrypt_batch": (i32, [vp, i32, i32, u8p, u64p, u8p, u64, u8p, u64p, u8p, u64, u8p, u8p]),
+    "capy_sponge_encrypt_batch_dev": (i32, [vp, i32, vp, i32, i32, u8p, u64p, u64, u8p, u64, u8p, u64p, u64, u8p, u8p]),
+    "capy_sponge_decrypt_batch_dev": (i32, [vp, i32, vp, i32, i32, u8p, u64p, u64, u8p, u64, u8p, u64p, u8p, u64, u8p,
+                                            u8p]),
+    "capy_ed448_key_encrypt_batch": (i32, [vp, i32, u8p, u8p, u8p, u64p, u64, u8p, u8p, u8p]),
+    "capy_ed448_key_decrypt_batch": (i32, [vp, i32, u8p, u64p, u8p, u8p, u64p, u8p, u64, u8p, u8p]),
+    "capy_ed448_key_encrypt_batch_dev": (i32, [vp, i32, vp, i32, u8p, u8p, u8p, u64p, u64, u8p, u8p, u8p, vp]),
+    "capy_ed448_key_decrypt_batch_dev": (i32, [vp, i32, vp, i32, u8p, u64p, u8p, u8p, u64p, u8p, u64, u8p, u8p, vp]),
 }
 
 

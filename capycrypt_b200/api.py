@@ -8,12 +8,15 @@ Same names, argument meaning and error behaviour as the reference:
   SpongeHashable                src/sha3/hashable.rs:7-36   compute_sha3_hash / compute_tagged_hash
   Signable                      src/ecc/signable.rs:12-15   sign / verify
   kmac_xof                      src/sha3/shake_functions.rs:79-89
+  SpongeEncryptable             src/sha3/encryptable.rs:7-10  sha3_encrypt / sha3_decrypt
+  KeyEncryptable                src/ecc/encryptable.rs:10-13  key_encrypt / key_decrypt
 Every function forwards to the CUDA engine through the C ABI; nothing is computed on the CPU.
 All operations work IN PLACE on the Message objects, like the reference.
 """
 from __future__ import annotations
 
 import datetime
+import os
 from dataclasses import dataclass, field
 from enum import IntEnum
 from typing import Optional, Sequence
@@ -153,6 +156,93 @@ class Gpu:
             for i, o in zip(idx, ok):
                 if not o:
                     res[i] = OperationError("SignatureVerificationFailure")
+        return res
+
+
+    # ---- SpongeEncryptable ---------------------------------------------------------------------------
+    def sha3_encrypt(self, msgs: Sequence[Message], pws: Sequence[bytes], d: SecParam,
+                     nonces: Optional[Sequence[bytes]] = None) -> None:
+        """Batched Message::sha3_encrypt (sha3/encryptable.rs:29-45): replaces .msg with the ciphertext, .digest with
+        the tag, .sym_nonce with z, .d with d.  z = 512 random bytes per message (get_random_bytes(512), :31), drawn
+        here on the host unless injected."""
+        d = SecParam.try_from(int(d))
+        if nonces is None:
+            nonces = [os.urandom(512) for _ in msgs]
+        pd, po = pack(pws)
+        md, mo = pack([m.msg for m in msgs])
+        ct, tag = self.engine.sponge_encrypt(pd, po, b"".join(nonces), 512, md, mo, int(d))
+        for i, m in enumerate(msgs):
+            m.msg = bytearray(ct[int(mo[i]):int(mo[i + 1])].tobytes())
+            m.digest = tag[i].tobytes()
+            m.sym_nonce = bytes(nonces[i])
+            m.d = d
+
+    def sha3_decrypt(self, msgs: Sequence[Message], pws: Sequence[bytes]) -> list[Optional[OperationError]]:
+        """Batched Message::sha3_decrypt (:58-83).  Per message None for Ok(()), else SecurityParameterNotSet /
+        SymNonceNotSet / SHA3DecryptionFailure; on failure .msg keeps the ciphertext."""
+        res: list[Optional[OperationError]] = [None] * len(msgs)
+        groups: dict[int, list[int]] = {}
+        for i, m in enumerate(msgs):
+            if m.d is None:
+                res[i] = OperationError("SecurityParameterNotSet")
+            elif m.sym_nonce is None:
+                res[i] = OperationError("SymNonceNotSet")
+            else:
+                groups.setdefault((int(m.d), len(m.sym_nonce)), []).append(i)
+        for (d, nl), idx in groups.items():
+            pd, po = pack([pws[i] for i in idx])
+            cd, co = pack([msgs[i].msg for i in idx])
+            tags = b"".join(bytes(msgs[i].digest).ljust(64, b"\0")[:64] for i in idx)
+            out, ok = self.engine.sponge_decrypt(pd, po, b"".join(msgs[i].sym_nonce for i in idx), nl, cd, co, tags, d)
+            for j, i in enumerate(idx):
+                good = bool(ok[j]) and len(msgs[i].digest) == 64
+                if good:
+                    msgs[i].msg = bytearray(out[int(co[j]):int(co[j + 1])].tobytes())
+                else:
+                    res[i] = OperationError("SHA3DecryptionFailure")
+        return res
+
+    # ---- KeyEncryptable ------------------------------------------------------------------------------
+    def key_encrypt(self, msgs: Sequence[Message], pub_keys: Sequence[bytes], d: SecParam,
+                    k_rand: Optional[Sequence[bytes]] = None) -> None:
+        """Batched Message::key_encrypt (ecc/encryptable.rs:34-50): .msg <- ciphertext, .digest <- tag (56 bytes),
+        .asym_nonce <- Z = [k]G (affine x || y), .d <- d.  k = 56 random bytes per message (:36) unless injected."""
+        d = SecParam.try_from(int(d))
+        if k_rand is None:
+            k_rand = [os.urandom(56) for _ in msgs]
+        md, mo = pack([m.msg for m in msgs])
+        rc, ct, tag, z = self.engine.ed448_key_encrypt(b"".join(pub_keys), b"".join(k_rand), md, mo, int(d))
+        if rc:
+            raise OperationError("InvalidPublicKey")
+        for i, m in enumerate(msgs):
+            m.msg = bytearray(ct[int(mo[i]):int(mo[i + 1])].tobytes())
+            m.digest = tag[i].tobytes()
+            m.asym_nonce = z[i].tobytes()
+            m.d = d
+
+    def key_decrypt(self, msgs: Sequence[Message], pws: Sequence[bytes]) -> list[Optional[OperationError]]:
+        """Batched Message::key_decrypt (:72-94): None for Ok(()), else SymNonceNotSet (sic, :73) /
+        SecurityParameterNotSet / KeyDecryptionError; on failure .msg keeps the ciphertext."""
+        res: list[Optional[OperationError]] = [None] * len(msgs)
+        groups: dict[int, list[int]] = {}
+        for i, m in enumerate(msgs):
+            if m.asym_nonce is None:
+                res[i] = OperationError("SymNonceNotSet")
+            elif m.d is None:
+                res[i] = OperationError("SecurityParameterNotSet")
+            else:
+                groups.setdefault(int(m.d), []).append(i)
+        for d, idx in groups.items():
+            pd, po = pack([pws[i] for i in idx])
+            cd, co = pack([msgs[i].msg for i in idx])
+            tags = b"".join(bytes(msgs[i].digest).ljust(56, b"\0")[:56] for i in idx)
+            _, out, ok = self.engine.ed448_key_decrypt(pd, po, b"".join(msgs[i].asym_nonce for i in idx), cd, co, tags, d)
+            for j, i in enumerate(idx):
+                good = bool(ok[j]) and len(msgs[i].digest) == 56
+                if good:
+                    msgs[i].msg = bytearray(out[int(co[j]):int(co[j + 1])].tobytes())
+                else:
+                    res[i] = OperationError("KeyDecryptionError")
         return res
 
 

@@ -17,7 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "_lib")
 LIB = os.path.join(LIBDIR, "libcapycrypt_gpu.so")
-SOURCES = ["ctx.cu", "sha3_api.cu", "ed448_api.cu", "ed448_fixed.cu", "ed448_var.cu"]
+SOURCES = ["ctx.cu", "sha3_api.cu", "ed448_api.cu", "ed448_fixed.cu", "ed448_var.cu", "ae_api.cu"]
 # per-source tuning, from measurements on B200 (profiles/README.md): the variable-base ladder is instruction-
 # cache bound when fully inlined (432 KB of code), so its field multiplications are out-of-line calls and
 # the kernel is capped at 128 registers (4 blocks/SM); the fixed-base comb is fastest fully inlined.

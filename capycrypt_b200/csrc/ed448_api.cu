@@ -137,7 +137,7 @@ __global__ void any_bad_kernel(const uint8_t* __restrict__ bad, int* bad_flag, u
 // ---- launch helpers ----------------------------------------------------------------------------------
 constexpr int kInvBatch = 16;
 
-static int launch_scalar_prep(capy_ctx* ctx, cudaStream_t st, const uint8_t* in, int mode, uint32_t* words, uint8_t* be,
+int launch_scalar_prep(capy_ctx* ctx, cudaStream_t st, const uint8_t* in, int mode, uint32_t* words, uint8_t* be,
                               uint64_t n) {
   scalar_prep_kernel<<<grid_for(n, 128), 128, 0, st>>>(in, mode, words, be, n);
   ctx->launches++;
@@ -145,7 +145,7 @@ static int launch_scalar_prep(capy_ctx* ctx, cudaStream_t st, const uint8_t* in,
   return CAPY_OK;
 }
 
-static int launch_to_affine(capy_ctx* ctx, cudaStream_t st, const uint32_t* proj, uint64_t n, int mode, const uint8_t* bad,
+int launch_to_affine(capy_ctx* ctx, cudaStream_t st, const uint32_t* proj, uint64_t n, int mode, const uint8_t* bad,
                             uint8_t* out) {
   const uint64_t threads = (n + kInvBatch - 1) / kInvBatch;
   to_affine_kernel<kInvBatch><<<grid_for(threads, 128), 128, 0, st>>>(proj, n, mode, bad, out);
@@ -215,7 +215,7 @@ static KmacDevArgs kmac_args(int d, const uint8_t* keys, const uint64_t* key_off
 }
 
 // s = 4 * BE(KMACXOF(pw, "", 448, "SK", d)) mod r  (ecc/keypair.rs:42-43): words + optional BE bytes
-static int dev_secret_scalar(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t st, int d, const uint8_t* d_pws,
+int dev_secret_scalar(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t st, int d, const uint8_t* d_pws,
                              const uint64_t* d_pw_off, uint64_t n, uint32_t* s_words, uint8_t* s_be) {
   CAPY_SCRATCH(tmp, uint8_t, SL_TMP56A, n * 56);
   int rc = launch_kmac_xof(ctx, dc, st, kmac_args(d, d_pws, d_pw_off, 0, nullptr, nullptr, n, "SK", tmp));

@@ -25,4 +25,10 @@ int launch_fixed_base(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t st, const uint3
 int launch_var_base(capy_ctx* ctx, cudaStream_t st, const uint8_t* scalars, int mode4, const uint8_t* points,
                     const uint32_t* addend, uint32_t* proj, uint8_t* bad, uint64_t n, bool constant_time);
 
+// ed448_api.cu
+int launch_scalar_prep(capy_ctx* ctx, cudaStream_t st, const uint8_t* in, int mode, uint32_t* words, uint8_t* be, uint64_t n);
+int launch_to_affine(capy_ctx* ctx, cudaStream_t st, const uint32_t* proj, uint64_t n, int mode, const uint8_t* bad, uint8_t* out);
+int dev_secret_scalar(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t st, int d, const uint8_t* d_pws, const uint64_t* d_pw_off,
+                      uint64_t n, uint32_t* s_words, uint8_t* s_be);
+
 }  // namespace capy

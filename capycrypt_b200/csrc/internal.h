@@ -14,7 +14,7 @@
 namespace capy {
 
 constexpr int kNumStreams = 3;
-constexpr int kNumScratch = 56;  // 0..17 sponge entry points, 24..55 Ed448 pipelines
+constexpr int kNumScratch = 80;  // 0..23 sponge entry points, 24..55 Ed448 pipelines, 56..79 AE pipelines
 
 // grow-only device scratch slots; each API call uses a fixed set of slot ids
 struct Scratch {
@@ -94,6 +94,7 @@ struct KmacDevArgs {
   const uint64_t* out_off;
   uint64_t out_stride;
   uint8_t* out;
+  const uint8_t* xor_in = nullptr;  // out = keystream ^ xor_in (same layout as out)
   bool no_sort = false;  // keep the caller's order (skips the length bucketing and its tiny D2H sync)
 };
 int launch_kmac_xof(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t stream, const KmacDevArgs& a);

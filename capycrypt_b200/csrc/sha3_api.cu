@@ -498,10 +498,15 @@ int launch_kmac_xof(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t stream, const Kma
   J.out_off = a.out_off;
   J.out_stride = a.out_stride;
   J.out_bytes = a.out_bytes;
+  J.xor_in = a.xor_in;
   J.n = a.n;
   LaunchPlan plan;
   if (a.off && !a.no_sort) {
     rc = plan_ragged(ctx, dc, stream, a.off, a.n, J.rate & ~7u, &plan);
+    if (rc) return rc;
+  } else if (!a.off && a.out_off && !a.no_sort) {
+    // keystream shape (sha3/encryptable.rs:41): the work of an item is its squeeze length
+    rc = plan_ragged(ctx, dc, stream, a.out_off, a.n, 8u * J.sq_lanes, &plan);
     if (rc) return rc;
   }
   J.order = plan.order;

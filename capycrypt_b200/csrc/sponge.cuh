@@ -58,6 +58,9 @@ struct SpongeJob {
   uint64_t out_stride;
   uint64_t out_bytes;
   uint32_t sq_lanes;  // lanes emitted per squeeze block = (1600 - d) / 64
+  // optional: out = squeeze XOR xor_in (same layout as out): keystream applied in place of a second pass
+  // (c = m ^ kmac_xof(ke, "", |m|, ...), sha3/encryptable.rs:41-42, ecc/encryptable.rs:45)
+  const uint8_t* xor_in;
   uint64_t n;
   // optional permutation of work: item index = order ? order[t] : t (length-sorted launch)
   const uint32_t* order;
@@ -280,17 +283,25 @@ __device__ __forceinline__ void sponge_item(const SpongeJob& J, uint64_t i) {
     out_bytes = J.out_bytes;
   }
   const uint64_t sq_bytes = 8ull * J.sq_lanes;
-  const bool o_aligned = (reinterpret_cast<uintptr_t>(o) & 7u) == 0;
+  const uint8_t* xi = J.xor_in ? J.xor_in + (o - J.out) : nullptr;
+  const bool o_aligned = (reinterpret_cast<uintptr_t>(o) & 7u) == 0 && (!xi || (reinterpret_cast<uintptr_t>(xi) & 7u) == 0);
   for (uint64_t produced = 0; produced < out_bytes;) {
 #pragma unroll
     for (int j = 0; j < 21; j++) {
       const uint64_t pos = produced + 8ull * j;
       if (j < (int)J.sq_lanes && pos < out_bytes) {
         if (o_aligned && pos + 8 <= out_bytes) {
-          *reinterpret_cast<uint2*>(o + pos) = make_uint2(a[j].lo, a[j].hi);
+          uint2 v = make_uint2(a[j].lo, a[j].hi);
+          if (xi) {
+            const uint2 m = *reinterpret_cast<const uint2*>(xi + pos);
+            v.x ^= m.x;
+            v.y ^= m.y;
+          }
+          *reinterpret_cast<uint2*>(o + pos) = v;
         } else {
           const uint64_t v = ((uint64_t)a[j].hi << 32) | a[j].lo;
-          for (int k = 0; k < 8 && pos + k < out_bytes; k++) o[pos + k] = (uint8_t)(v >> (8 * k));
+          for (int k = 0; k < 8 && pos + k < out_bytes; k++)
+            o[pos + k] = (uint8_t)(v >> (8 * k)) ^ (xi ? xi[pos + k] : (uint8_t)0);
         }
       }
     }

@@ -189,6 +189,48 @@ class Engine:
                          allow=(B.ERR_BAD_POINT,))
         return rc, wx, z
 
+    def sponge_encrypt(self, pws, pw_off, nonces, nonce_len: int, msgs, msg_off, d: int, variant: int = B.AE_SHA3):
+        """-> (ciphertext packed like msgs, tags n x 64)."""
+        pws, pw_off, nonces, msgs, msg_off = _u8(pws), _u64(pw_off), _u8(nonces), _u8(msgs), _u64(msg_off)
+        n = len(msg_off) - 1
+        ct = np.zeros(len(msgs), dtype=np.uint8)
+        tag = np.zeros((n, 64), dtype=np.uint8)
+        self._check(self.lib.capy_sponge_encrypt_batch(self._ctx, d, variant, _hp(pws), _hp(pw_off), _hp(nonces), nonce_len,
+                                                       _hp(msgs), _hp(msg_off), n, _hp(ct), _hp(tag)))
+        return ct, tag
+
+    def sponge_decrypt(self, pws, pw_off, nonces, nonce_len: int, ct, ct_off, tags, d: int, variant: int = B.AE_SHA3):
+        """-> (buffer packed like ct, ok n)."""
+        pws, pw_off, nonces, ct, ct_off, tags = _u8(pws), _u64(pw_off), _u8(nonces), _u8(ct), _u64(ct_off), _u8(tags)
+        n = len(ct_off) - 1
+        out = np.zeros(len(ct), dtype=np.uint8)
+        ok = np.zeros(n, dtype=np.uint8)
+        self._check(self.lib.capy_sponge_decrypt_batch(self._ctx, d, variant, _hp(pws), _hp(pw_off), _hp(nonces), nonce_len,
+                                                       _hp(ct), _hp(ct_off), _hp(tags), n, _hp(out), _hp(ok)))
+        return out, ok
+
+    def ed448_key_encrypt(self, pub_xy112, k_rand56, msgs, msg_off, d: int):
+        """-> (rc, ciphertext, tags n x 56, nonce points Z n x 112)."""
+        pub, k, msgs, msg_off = _u8(pub_xy112), _u8(k_rand56), _u8(msgs), _u64(msg_off)
+        n = len(msg_off) - 1
+        ct = np.zeros(len(msgs), dtype=np.uint8)
+        tag = np.zeros((n, 56), dtype=np.uint8)
+        z = np.zeros((n, 112), dtype=np.uint8)
+        rc = self._check(self.lib.capy_ed448_key_encrypt_batch(self._ctx, d, _hp(pub), _hp(k), _hp(msgs), _hp(msg_off), n,
+                                                               _hp(ct), _hp(tag), _hp(z)), allow=(B.ERR_BAD_POINT,))
+        return rc, ct, tag, z
+
+    def ed448_key_decrypt(self, pws, pw_off, z_xy112, ct, ct_off, tags, d: int):
+        """-> (rc, buffer packed like ct, ok n)."""
+        pws, pw_off, z, ct, ct_off, tags = _u8(pws), _u64(pw_off), _u8(z_xy112), _u8(ct), _u64(ct_off), _u8(tags)
+        n = len(ct_off) - 1
+        out = np.zeros(len(ct), dtype=np.uint8)
+        ok = np.zeros(n, dtype=np.uint8)
+        rc = self._check(self.lib.capy_ed448_key_decrypt_batch(self._ctx, d, _hp(pws), _hp(pw_off), _hp(z), _hp(ct),
+                                                               _hp(ct_off), _hp(tags), n, _hp(out), _hp(ok)),
+                         allow=(B.ERR_BAD_POINT,))
+        return rc, out, ok
+
     # =================================================================================
     # device-pointer API (async on torch's current stream); tensors are torch.uint8 / int64 CUDA
     # =================================================================================
@@ -273,3 +315,33 @@ class Engine:
                                                          t_z.data_ptr(), n, t_ok.data_ptr(),
                                                          t_bad.data_ptr() if t_bad is not None else None))
         return t_ok
+
+    def sponge_encrypt_dev(self, t_pws, t_pw_off, pw_bytes: int, t_nonces, nonce_len: int, t_msgs, t_msg_off, d: int, t_ct,
+                           t_tag, variant: int = B.AE_SHA3, dev_index: int = 0):
+        n = t_msg_off.numel() - 1
+        self._check(self.lib.capy_sponge_encrypt_batch_dev(
+            self._ctx, dev_index, self._stream(), d, variant, t_pws.data_ptr(), t_pw_off.data_ptr(), pw_bytes,
+            t_nonces.data_ptr(), nonce_len, t_msgs.data_ptr(), t_msg_off.data_ptr(), n, t_ct.data_ptr(), t_tag.data_ptr()))
+
+    def sponge_decrypt_dev(self, t_pws, t_pw_off, pw_bytes: int, t_nonces, nonce_len: int, t_ct, t_ct_off, t_tag, d: int,
+                           t_out, t_ok, variant: int = B.AE_SHA3, dev_index: int = 0):
+        n = t_ct_off.numel() - 1
+        self._check(self.lib.capy_sponge_decrypt_batch_dev(
+            self._ctx, dev_index, self._stream(), d, variant, t_pws.data_ptr(), t_pw_off.data_ptr(), pw_bytes,
+            t_nonces.data_ptr(), nonce_len, t_ct.data_ptr(), t_ct_off.data_ptr(), t_tag.data_ptr(), n, t_out.data_ptr(),
+            t_ok.data_ptr()))
+
+    def ed448_key_encrypt_dev(self, t_pub, t_k, t_msgs, t_msg_off, d: int, t_ct, t_tag, t_z, t_bad=None, dev_index: int = 0):
+        n = t_msg_off.numel() - 1
+        self._check(self.lib.capy_ed448_key_encrypt_batch_dev(
+            self._ctx, dev_index, self._stream(), d, t_pub.data_ptr(), t_k.data_ptr(), t_msgs.data_ptr(),
+            t_msg_off.data_ptr(), n, t_ct.data_ptr(), t_tag.data_ptr(), t_z.data_ptr(),
+            t_bad.data_ptr() if t_bad is not None else None))
+
+    def ed448_key_decrypt_dev(self, t_pws, t_pw_off, t_z, t_ct, t_ct_off, t_tag, d: int, t_out, t_ok, t_bad=None,
+                              dev_index: int = 0):
+        n = t_ct_off.numel() - 1
+        self._check(self.lib.capy_ed448_key_decrypt_batch_dev(
+            self._ctx, dev_index, self._stream(), d, t_pws.data_ptr(), t_pw_off.data_ptr(), t_z.data_ptr(),
+            t_ct.data_ptr(), t_ct_off.data_ptr(), t_tag.data_ptr(), n, t_out.data_ptr(), t_ok.data_ptr(),
+            t_bad.data_ptr() if t_bad is not None else None))

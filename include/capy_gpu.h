@@ -160,6 +160,52 @@ int capy_ed448_verify_batch_dev(capy_ctx* ctx, int dev_index, void* stream, int 
 int capy_ed448_ecdh_batch(capy_ctx* ctx, const uint8_t* k_rand56, const uint8_t* pub_xy112, uint64_t n,
                           uint8_t* wx56, uint8_t* z_xy112);
 
+/* ---- Sponge AE : SpongeEncryptable::sha3_encrypt / sha3_decrypt (sha3/encryptable.rs:29-45, 58-83) and the
+ *      symmetric half of KEMEncryptable::kem_encrypt / kem_decrypt (kem/encryptable.rs:51-57, 91-104, where
+ *      `pw` is the ML-KEM shared secret; ML-KEM itself is out of scope) --------------------------------- */
+#define CAPY_AE_SHA3 0 /* customisation strings "S", "SKE", "SKA" */
+#define CAPY_AE_KEM 1  /* "S", "KEMKE", "KEMKA" */
+/* (ke || ka) = KMACXOF(z_i || pw_i, "", 1024, "S"); tag64[i] = KMACXOF(ka, m_i, 512, KA);
+ * ct_i = KMACXOF(ke, "", |m_i|, KE) xor m_i, written at the message's own offsets (|ct| == |m|).
+ * nonces: n * nonce_len bytes (the reference draws nonce_len = 512 random BYTES, :31); no RNG inside. */
+int capy_sponge_encrypt_batch(capy_ctx* ctx, int d_bits, int variant, const uint8_t* pws, const uint64_t* pw_off,
+                              const uint8_t* nonces, uint64_t nonce_len, const uint8_t* msgs, const uint64_t* msg_off,
+                              uint64_t n, uint8_t* ct, uint8_t* tag64);
+/* ok[i] = 1 for Ok(()); 0 = OperationError::SHA3DecryptionFailure, and out_i is then the ciphertext again
+ * (the reference XORs the keystream back, :77-82).  `out` must not alias `ct`. */
+int capy_sponge_decrypt_batch(capy_ctx* ctx, int d_bits, int variant, const uint8_t* pws, const uint64_t* pw_off,
+                              const uint8_t* nonces, uint64_t nonce_len, const uint8_t* ct, const uint64_t* ct_off,
+                              const uint8_t* tag64, uint64_t n, uint8_t* out, uint8_t* ok);
+/* device twins; pw_bytes = total bytes in d_pws (sizes the z || pw key buffer) */
+int capy_sponge_encrypt_batch_dev(capy_ctx* ctx, int dev_index, void* stream, int d_bits, int variant, const uint8_t* d_pws,
+                                  const uint64_t* d_pw_off, uint64_t pw_bytes, const uint8_t* d_nonces, uint64_t nonce_len,
+                                  const uint8_t* d_msgs, const uint64_t* d_msg_off, uint64_t n, uint8_t* d_ct,
+                                  uint8_t* d_tag64);
+int capy_sponge_decrypt_batch_dev(capy_ctx* ctx, int dev_index, void* stream, int d_bits, int variant, const uint8_t* d_pws,
+                                  const uint64_t* d_pw_off, uint64_t pw_bytes, const uint8_t* d_nonces, uint64_t nonce_len,
+                                  const uint8_t* d_ct, const uint64_t* d_ct_off, const uint8_t* d_tag64, uint64_t n,
+                                  uint8_t* d_out, uint8_t* d_ok);
+
+/* ---- ECDHIES : KeyEncryptable::key_encrypt / key_decrypt (ecc/encryptable.rs:34-50, 72-94) ---------------- */
+/* k_i = 4 * BE(k_rand56[i]) mod r; W = [k]V_i; z_xy112[i] = [k]G (Message.asym_nonce, affine);
+ * (ke || ka) = KMACXOF(W.x, "", 896, "PK"); tag56[i] = KMACXOF(ka, m_i, 448, "PKA");
+ * ct_i = KMACXOF(ke, "", |m_i|, "PKE") xor m_i.  Off-curve V_i -> CAPY_ERR_BAD_POINT (W.x taken as 0). */
+int capy_ed448_key_encrypt_batch(capy_ctx* ctx, int d_bits, const uint8_t* pub_xy112, const uint8_t* k_rand56,
+                                 const uint8_t* msgs, const uint64_t* msg_off, uint64_t n, uint8_t* ct, uint8_t* tag56,
+                                 uint8_t* z_xy112);
+/* s = 4 * BE(KMACXOF(pw, "", 448, "SK")) mod r; W = [s]Z_i; ok[i] = 1 for Ok(()), 0 = KeyDecryptionError with
+ * out_i = ciphertext (:88-93).  `out` must not alias `ct`. */
+int capy_ed448_key_decrypt_batch(capy_ctx* ctx, int d_bits, const uint8_t* pws, const uint64_t* pw_off,
+                                 const uint8_t* z_xy112, const uint8_t* ct, const uint64_t* ct_off, const uint8_t* tag56,
+                                 uint64_t n, uint8_t* out, uint8_t* ok);
+int capy_ed448_key_encrypt_batch_dev(capy_ctx* ctx, int dev_index, void* stream, int d_bits, const uint8_t* d_pub_xy112,
+                                     const uint8_t* d_k_rand56, const uint8_t* d_msgs, const uint64_t* d_msg_off, uint64_t n,
+                                     uint8_t* d_ct, uint8_t* d_tag56, uint8_t* d_z_xy112, int* d_bad_flag);
+int capy_ed448_key_decrypt_batch_dev(capy_ctx* ctx, int dev_index, void* stream, int d_bits, const uint8_t* d_pws,
+                                     const uint64_t* d_pw_off, const uint8_t* d_z_xy112, const uint8_t* d_ct,
+                                     const uint64_t* d_ct_off, const uint8_t* d_tag56, uint64_t n, uint8_t* d_out,
+                                     uint8_t* d_ok, int* d_bad_flag);
+
 #ifdef __cplusplus
 }
 #endif
