@@ -20,9 +20,22 @@ out = torch.zeros(n * 112, dtype=torch.uint8, device="cuda")
 ms = timeit(lambda: eng.ed448_fixed_base_dev(sc, n, out))
 res["fixed_2^20_ms"] = round(ms, 3); res["fixed_Mps"] = round(n / ms / 1e3, 2)
 res["fixed_digest"] = hashlib.sha256(out[: 112 * 4096].cpu().numpy().tobytes()).hexdigest()[:12]
-n2 = 1 << 18
+n2 = int(os.environ.get('VB_N', 1 << 18))
 out2 = torch.zeros(n2 * 112, dtype=torch.uint8, device="cuda")
 ms = timeit(lambda: eng.ed448_var_base_dev(sc, out, n2, out2), reps=2)
-res["var_2^18_ms"] = round(ms, 3); res["var_Mps"] = round(n2 / ms / 1e3, 2)
+res["var_n"] = n2; res["var_2^18_ms"] = round(ms, 3); res["var_Mps"] = round(n2 / ms / 1e3, 2)
 res["var_digest"] = hashlib.sha256(out2[: 112 * 4096].cpu().numpy().tobytes()).hexdigest()[:12]
+print(json.dumps(res))
+# verify pipeline (public inputs: direct table lookups), 2^17 items x 64 B messages
+n3 = 1 << 17
+pw = torch.randint(0, 256, (n3 * 16,), dtype=torch.uint8, device="cuda", generator=g)
+pw_off = torch.arange(0, n3 + 1, dtype=torch.int64, device="cuda") * 16
+msg = torch.randint(0, 256, (n3 * 64,), dtype=torch.uint8, device="cuda", generator=g)
+msg_off = torch.arange(0, n3 + 1, dtype=torch.int64, device="cuda") * 64
+pub = torch.zeros(n3 * 112, dtype=torch.uint8, device="cuda")
+h = torch.zeros(n3 * 56, dtype=torch.uint8, device="cuda"); z = torch.zeros(n3 * 56, dtype=torch.uint8, device="cuda")
+ok = torch.zeros(n3, dtype=torch.uint8, device="cuda")
+eng.ed448_keygen_dev(pw, pw_off, 512, pub); eng.ed448_sign_dev(pw, pw_off, msg, msg_off, 512, h, z)
+ms = timeit(lambda: eng.ed448_verify_dev(pub, msg, msg_off, h, z, 512, ok), reps=2)
+res["verify_2^17_ms"] = round(ms, 3); res["verify_Mps"] = round(n3 / ms / 1e3, 2); res["verify_all_ok"] = bool(ok.all().item())
 print(json.dumps(res))

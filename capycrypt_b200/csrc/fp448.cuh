@@ -37,7 +37,7 @@ namespace capy {
 
 constexpr uint32_t M28 = (1u << 28) - 1u;
 
-struct Fe {
+struct alignas(16) Fe {
   uint32_t v[16];
 };
 
@@ -115,6 +115,20 @@ CAPY_HD void fe_carry_wide(Fe& r, const uint64_t (&R)[16]) {
   fe_weak(r);
 }
 
+// end of the two in-order carry chains of fe_mul / fe_sqr: v = limbs < 2^28, clo = carry out of limb 7 (weight
+// 2^224, goes to limb 8), chi = carry out of limb 15 (weight 2^448 = 2^224 + 1, goes to limbs 0 and 8); both
+// < 2^37.  One more step on limbs 0 and 8 leaves every limb below 2^28 + 2^10 (tight).
+CAPY_HD void fe_carry_tail(Fe& r, uint32_t (&v)[16], uint64_t clo, uint64_t chi) {
+  const uint64_t t0 = (uint64_t)v[0] + chi;
+  const uint64_t t8 = (uint64_t)v[8] + clo + chi;
+  v[0] = (uint32_t)t0 & M28;
+  v[1] += (uint32_t)(t0 >> 28);
+  v[8] = (uint32_t)t8 & M28;
+  v[9] += (uint32_t)(t8 >> 28);
+#pragma unroll
+  for (int i = 0; i < 16; i++) r.v[i] = v[i];
+}
+
 // widening multiplies: unsigned for sums of limbs (may reach 2^32 - 1), signed only for the
 // negated a0 limbs (|.| < 2^31).  Both are one IMAD.WIDE; accumulation is mod 2^64.
 CAPY_HD uint64_t mulu(uint32_t a, uint32_t b) { return (uint64_t)a * b; }
@@ -137,7 +151,10 @@ CAPY_HD void fe_mul_inl(Fe& r, const Fe& a, const Fe& b) {
   // with U = a0*b0, W = a1*b1, Y = s*t as 15-column products (lo = columns 0..7, hi = 8..14):
   //   r[k]     = Ulo[k] + Wlo[k] + Yhi[k] - Uhi[k]
   //   r[8 + k] = Whi[k] + Yhi[k] + Ylo[k] - Ulo[k]
-  uint64_t R[16];
+  // Columns k and 8 + k are finished together and in order, so the carry of the two limb chains 0..7 and
+  // 8..15 is resolved on the fly: one AND and one 64-bit shift per column, no separate carry pass.
+  uint32_t v[16];
+  uint64_t clo = 0, chi = 0;
 #pragma unroll
   for (int k = 0; k < 8; k++) {
     uint64_t z = 0, u = 0;
@@ -145,7 +162,7 @@ CAPY_HD void fe_mul_inl(Fe& r, const Fe& a, const Fe& b) {
     for (int i = k + 1; i < 8; i++) z += mulu(s[i], t[k + 8 - i]);  // Yhi[k]
 #pragma unroll
     for (int i = 0; i <= k; i++) u += mulu(a0[i], b0[k - i]);  // Ulo[k]
-    uint64_t lo = z + u, hi = z - u;
+    uint64_t lo = z + u + clo, hi = z - u + chi;  // the carries ride on the additions that are needed anyway
 #pragma unroll
     for (int i = 0; i <= k; i++) lo += mulu(a1[i], b1[k - i]);  // Wlo[k]
 #pragma unroll
@@ -154,10 +171,12 @@ CAPY_HD void fe_mul_inl(Fe& r, const Fe& a, const Fe& b) {
     for (int i = k + 1; i < 8; i++) hi += mulu(a1[i], b1[k + 8 - i]);  // Whi[k]
 #pragma unroll
     for (int i = 0; i <= k; i++) hi += mulu(s[i], t[k - i]);  // Ylo[k]
-    R[k] = lo;
-    R[8 + k] = hi;
+    v[k] = (uint32_t)lo & M28;
+    clo = lo >> 28;
+    v[8 + k] = (uint32_t)hi & M28;
+    chi = hi >> 28;
   }
-  fe_carry_wide(r, R);
+  fe_carry_tail(r, v, clo, chi);
 }
 
 // r = a^2.  Requires alpha_a^2 <= 6.
@@ -176,7 +195,8 @@ CAPY_HD void fe_sqr_inl(Fe& r, const Fe& a) {
     na0[i] = -(int32_t)a0[i];
   }
   // column m of x^2 = sum_{i<j, i+j=m} (2 x_i) x_j + [m even] x_{m/2}^2
-  uint64_t R[16];
+  uint32_t v[16];
+  uint64_t clo = 0, chi = 0;
 #pragma unroll
   for (int k = 0; k < 8; k++) {
     uint64_t z = 0, u = 0;
@@ -192,7 +212,7 @@ CAPY_HD void fe_sqr_inl(Fe& r, const Fe& a) {
       if (i < j) u += mulu(d0[i], a0[j]);
       if (i == j) u += mulu(a0[i], a0[i]);
     }
-    uint64_t lo = z + u, hi = z - u;
+    uint64_t lo = z + u + clo, hi = z - u + chi;
 #pragma unroll
     for (int i = 0; i <= k; i++) {  // Wlo[k]
       const int j = k - i;
@@ -217,10 +237,12 @@ CAPY_HD void fe_sqr_inl(Fe& r, const Fe& a) {
       if (i < j) hi += mulu(ds[i], s[j]);
       if (i == j) hi += mulu(s[i], s[i]);
     }
-    R[k] = lo;
-    R[8 + k] = hi;
+    v[k] = (uint32_t)lo & M28;
+    clo = lo >> 28;
+    v[8 + k] = (uint32_t)hi & M28;
+    chi = hi >> 28;
   }
-  fe_carry_wide(r, R);
+  fe_carry_tail(r, v, clo, chi);
 }
 
 // out-of-line copies: one body instead of ~450 inlined instructions per call site.  Always used by

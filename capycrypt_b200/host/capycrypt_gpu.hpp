@@ -5,10 +5,12 @@
 //   capycrypt::Message         src/lib.rs:65-94          capycrypt::Signature       src/ecc/signable.rs:17-24
 //   capycrypt::KeyPair         src/ecc/keypair.rs:13-51
 //   capycrypt::gpu::Engine     batch forms of SpongeHashable (sha3/hashable.rs:7-36), kmac_xof
-//                              (sha3/shake_functions.rs:79-89), KeyPair::new, Signable (ecc/signable.rs:12-15)
+//                              (sha3/shake_functions.rs:79-89), KeyPair::new, Signable (ecc/signable.rs:12-15),
+//                              SpongeEncryptable (sha3/encryptable.rs:7-10), KeyEncryptable (ecc/encryptable.rs:10-13)
 // Header-only; link with -lcapycrypt_gpu.  Nothing is computed on the CPU.
 #pragma once
 #include <array>
+#include <random>
 #include <cstdint>
 #include <optional>
 #include <stdexcept>
@@ -26,6 +28,8 @@ enum class OperationError {  // src/lib.rs:9-30 (the variants the hot path can p
   SignatureNotSet,
   KeyDecryptionError,
   BytesToScalarError,
+  SHA3DecryptionFailure,
+  SymNonceNotSet,
 };
 
 enum class SecParam : int { D224 = 224, D256 = 256, D384 = 384, D512 = 512 };
@@ -198,6 +202,134 @@ class Engine {
       if (rc != CAPY_OK && rc != CAPY_ERR_BAD_POINT) check(rc);
       for (size_t k = 0; k < idx.size(); k++)
         if (!ok[k]) res[idx[k]] = OperationError::SignatureVerificationFailure;
+    }
+    return res;
+  }
+
+  // SpongeEncryptable::sha3_encrypt (sha3/encryptable.rs:29-45): msg <- ciphertext, digest <- tag, sym_nonce <- z.
+  // z = 512 random bytes per message (:31) drawn on the host unless `nonces` is given.
+  std::optional<OperationError> sha3_encrypt(std::vector<Message>& msgs, const std::vector<Bytes>& pws, int d_bits,
+                                             const std::vector<Bytes>* nonces = nullptr) {
+    if (!sec_param_try_from(d_bits)) return OperationError::UnsupportedSecurityParameter;
+    const size_t n = msgs.size();
+    Bytes pd, md, zs(n * 512 + 1);
+    std::vector<uint64_t> po, mo;
+    detail::pack(pws, [](const Bytes& b) -> const Bytes& { return b; }, pd, po);
+    detail::pack(msgs, [](const Message& m) -> const Bytes& { return m.msg; }, md, mo);
+    std::random_device rd;
+    for (size_t i = 0; i < n; i++)
+      for (size_t k = 0; k < 512; k++) zs[512 * i + k] = nonces ? (*nonces)[i][k] : (uint8_t)rd();
+    Bytes ct(md.size()), tag(n * 64 + 1);
+    check(capy_sponge_encrypt_batch(ctx_, d_bits, CAPY_AE_SHA3, pd.data(), po.data(), zs.data(), 512, md.data(), mo.data(), n,
+                                    ct.data(), tag.data()));
+    for (size_t i = 0; i < n; i++) {
+      msgs[i].msg.assign(ct.begin() + mo[i], ct.begin() + mo[i + 1]);
+      msgs[i].digest.assign(tag.begin() + 64 * i, tag.begin() + 64 * (i + 1));
+      msgs[i].sym_nonce = Bytes(zs.begin() + 512 * i, zs.begin() + 512 * (i + 1));
+      msgs[i].d = *sec_param_try_from(d_bits);
+    }
+    return std::nullopt;
+  }
+
+  // SpongeEncryptable::sha3_decrypt (:58-83): empty for Ok(()); on failure msg keeps the ciphertext
+  std::vector<std::optional<OperationError>> sha3_decrypt(std::vector<Message>& msgs, const std::vector<Bytes>& pws) {
+    std::vector<std::optional<OperationError>> res(msgs.size());
+    for (int d_bits : {224, 256, 384, 512}) {
+      std::vector<size_t> idx;
+      for (size_t i = 0; i < msgs.size(); i++) {
+        if (!msgs[i].d) res[i] = OperationError::SecurityParameterNotSet;
+        else if (!msgs[i].sym_nonce) res[i] = OperationError::SymNonceNotSet;
+        else if ((int)*msgs[i].d == d_bits) {
+          if (msgs[i].sym_nonce->size() != 512 || msgs[i].digest.size() != 64) res[i] = OperationError::SHA3DecryptionFailure;
+          else idx.push_back(i);
+        }
+      }
+      if (idx.empty()) continue;
+      Bytes pd, cd, zs, tags;
+      std::vector<uint64_t> po(1, 0), co(1, 0);
+      for (size_t i : idx) {
+        pd.insert(pd.end(), pws[i].begin(), pws[i].end());
+        po.push_back(pd.size());
+        cd.insert(cd.end(), msgs[i].msg.begin(), msgs[i].msg.end());
+        co.push_back(cd.size());
+        zs.insert(zs.end(), msgs[i].sym_nonce->begin(), msgs[i].sym_nonce->end());
+        tags.insert(tags.end(), msgs[i].digest.begin(), msgs[i].digest.end());
+      }
+      if (pd.empty()) pd.push_back(0);
+      if (cd.empty()) cd.push_back(0);
+      Bytes out(cd.size()), ok(idx.size());
+      check(capy_sponge_decrypt_batch(ctx_, d_bits, CAPY_AE_SHA3, pd.data(), po.data(), zs.data(), 512, cd.data(), co.data(),
+                                      tags.data(), idx.size(), out.data(), ok.data()));
+      for (size_t k = 0; k < idx.size(); k++) {
+        if (ok[k]) msgs[idx[k]].msg.assign(out.begin() + co[k], out.begin() + co[k + 1]);
+        else res[idx[k]] = OperationError::SHA3DecryptionFailure;
+      }
+    }
+    return res;
+  }
+
+  // KeyEncryptable::key_encrypt (ecc/encryptable.rs:34-50): msg <- ciphertext, digest <- tag, asym_nonce <- Z.
+  // k = 56 random bytes per message (:36) drawn on the host unless `k_rand` is given.
+  std::optional<OperationError> key_encrypt(std::vector<Message>& msgs, const std::vector<AffinePoint>& pubs, int d_bits,
+                                            const std::vector<std::array<uint8_t, 56>>* k_rand = nullptr) {
+    if (!sec_param_try_from(d_bits)) return OperationError::UnsupportedSecurityParameter;
+    const size_t n = msgs.size();
+    Bytes md, pub(n * 112 + 1), ks(n * 56 + 1);
+    std::vector<uint64_t> mo;
+    detail::pack(msgs, [](const Message& m) -> const Bytes& { return m.msg; }, md, mo);
+    std::random_device rd;
+    for (size_t i = 0; i < n; i++) {
+      std::copy(pubs[i].begin(), pubs[i].end(), pub.begin() + 112 * i);
+      for (size_t k = 0; k < 56; k++) ks[56 * i + k] = k_rand ? (*k_rand)[i][k] : (uint8_t)rd();
+    }
+    Bytes ct(md.size()), tag(n * 56 + 1), z(n * 112 + 1);
+    check(capy_ed448_key_encrypt_batch(ctx_, d_bits, pub.data(), ks.data(), md.data(), mo.data(), n, ct.data(), tag.data(),
+                                       z.data()));
+    for (size_t i = 0; i < n; i++) {
+      msgs[i].msg.assign(ct.begin() + mo[i], ct.begin() + mo[i + 1]);
+      msgs[i].digest.assign(tag.begin() + 56 * i, tag.begin() + 56 * (i + 1));
+      AffinePoint zp;
+      std::copy(z.begin() + 112 * i, z.begin() + 112 * (i + 1), zp.begin());
+      msgs[i].asym_nonce = zp;
+      msgs[i].d = *sec_param_try_from(d_bits);
+    }
+    return std::nullopt;
+  }
+
+  // KeyEncryptable::key_decrypt (:72-94): empty for Ok(()); SymNonceNotSet (sic, :73) when asym_nonce is missing
+  std::vector<std::optional<OperationError>> key_decrypt(std::vector<Message>& msgs, const std::vector<Bytes>& pws) {
+    std::vector<std::optional<OperationError>> res(msgs.size());
+    for (int d_bits : {224, 256, 384, 512}) {
+      std::vector<size_t> idx;
+      for (size_t i = 0; i < msgs.size(); i++) {
+        if (!msgs[i].asym_nonce) res[i] = OperationError::SymNonceNotSet;
+        else if (!msgs[i].d) res[i] = OperationError::SecurityParameterNotSet;
+        else if ((int)*msgs[i].d == d_bits) {
+          if (msgs[i].digest.size() != 56) res[i] = OperationError::KeyDecryptionError;
+          else idx.push_back(i);
+        }
+      }
+      if (idx.empty()) continue;
+      Bytes pd, cd, zs, tags;
+      std::vector<uint64_t> po(1, 0), co(1, 0);
+      for (size_t i : idx) {
+        pd.insert(pd.end(), pws[i].begin(), pws[i].end());
+        po.push_back(pd.size());
+        cd.insert(cd.end(), msgs[i].msg.begin(), msgs[i].msg.end());
+        co.push_back(cd.size());
+        zs.insert(zs.end(), msgs[i].asym_nonce->begin(), msgs[i].asym_nonce->end());
+        tags.insert(tags.end(), msgs[i].digest.begin(), msgs[i].digest.end());
+      }
+      if (pd.empty()) pd.push_back(0);
+      if (cd.empty()) cd.push_back(0);
+      Bytes out(cd.size()), ok(idx.size());
+      int rc = capy_ed448_key_decrypt_batch(ctx_, d_bits, pd.data(), po.data(), zs.data(), cd.data(), co.data(), tags.data(),
+                                            idx.size(), out.data(), ok.data());
+      if (rc != CAPY_OK && rc != CAPY_ERR_BAD_POINT) check(rc);
+      for (size_t k = 0; k < idx.size(); k++) {
+        if (ok[k]) msgs[idx[k]].msg.assign(out.begin() + co[k], out.begin() + co[k + 1]);
+        else res[idx[k]] = OperationError::KeyDecryptionError;
+      }
     }
     return res;
   }

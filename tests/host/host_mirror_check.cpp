@@ -54,6 +54,39 @@ int main() {
   Message unsigned_msg(Bytes{1, 2, 3});
   r = eng.verify({unsigned_msg}, {keys[0].pub_key});
   EXPECT(r[0] == OperationError::SignatureNotSet);
+  // test_symmetric_encryptable (tests/integration_tests.rs:96-114, SHA3 half) + decryption_test (:250-262)
+  {
+    std::vector<Message> e;
+    e.emplace_back(Bytes(5242, 0x5a));
+    e.emplace_back(Bytes{});
+    std::vector<Bytes> pw = {Bytes(64, 1), Bytes(3, 2)};
+    const Bytes plain0 = e[0].msg;
+    EXPECT(!eng.sha3_encrypt(e, pw, 512));
+    EXPECT(e[0].msg != plain0 && e[0].msg.size() == plain0.size() && e[0].digest.size() == 64 && e[0].sym_nonce->size() == 512);
+    const Bytes enc0 = e[0].msg;
+    auto bad = eng.sha3_decrypt(e, {Bytes(64, 3), pw[1]});
+    EXPECT(bad[0] == OperationError::SHA3DecryptionFailure && !bad[1] && e[0].msg == enc0);
+    auto good = eng.sha3_decrypt(e, pw);
+    EXPECT(!good[0] && !good[1] && e[0].msg == plain0);
+    Message no_d(Bytes{1});
+    std::vector<Message> nd = {no_d};
+    EXPECT(eng.sha3_decrypt(nd, {Bytes{}})[0] == OperationError::SecurityParameterNotSet);
+  }
+  // test_key_gen_enc_dec_512 (:44-60) + test_key_decrypt_handling_bad_input (:268-281)
+  {
+    std::vector<Message> e;
+    e.emplace_back(Bytes(5242, 0x33));
+    e.emplace_back(Bytes(125, 0x44));
+    const Bytes plain0 = e[0].msg, plain1 = e[1].msg;
+    EXPECT(!eng.key_encrypt(e, {keys[0].pub_key, keys[1].pub_key}, 512));
+    EXPECT(e[0].msg != plain0 && e[0].digest.size() == 56 && e[0].asym_nonce.has_value());
+    const Bytes enc0 = e[0].msg, enc1 = e[1].msg;
+    auto bad = eng.key_decrypt(e, {pws[1], pws[0]});
+    EXPECT(bad[0] == OperationError::KeyDecryptionError && bad[1] == OperationError::KeyDecryptionError);
+    EXPECT(e[0].msg == enc0 && e[1].msg == enc1);
+    auto good = eng.key_decrypt(e, pws);
+    EXPECT(!good[0] && !good[1] && e[0].msg == plain0 && e[1].msg == plain1);
+  }
   printf("host mirror ok\n");
   return 0;
 }

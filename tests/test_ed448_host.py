@@ -54,6 +54,18 @@ def test_field_ops(host):
         assert _fe(host, 5, a, b) == (a + b) * (a - b) % P  # loose (unreduced) operands into the multiplier
 
 
+def test_field_ops_worst_case_limbs(host):
+    """All-ones 28-bit limbs (every limb at its maximum) through the multiplier at the loosest operand bounds the
+    point formulas use (2 x 3): the 64-bit column sums and the in-order carry chains must not overflow."""
+    ones = int("fffffff" * 16, 16)
+    hi = (1 << 448) - 1
+    for a in (ones, hi, P - 1, ones - 1):
+        for b in (ones, hi, 0, 1, P - 1):
+            assert _fe(host, 0, a, b) == a * b % P
+            assert _fe(host, 1, a) == a * a % P
+            assert _fe(host, 5, a, b) == (a + b) * (a - b) % P
+
+
 def test_field_inverse(host):
     rnd = random.Random(2)
     for a in EDGE_FE + [rnd.randrange(P) for _ in range(20)]:
