@@ -450,6 +450,63 @@ def extras(eng, dev, peaks, world, dist, rank):
     out["ed448_schnorr_2^18x256B"] = {
         "keygens_per_s": world * n4 / (ms_k * 1e-3), "signs_per_s": world * n4 / (ms_s * 1e-3),
         "verifies_per_s": world * n4 / (ms_v * 1e-3), "ms_keygen": ms_k, "ms_sign": ms_s, "ms_verify": ms_v}
+
+    # "next" rows N2 / N3: sponge AE over the cfg-2 shape (2^16 x 4 KB: two 4 KB KMAC passes per message,
+    # one absorbing, one squeezing into the XOR) and ECDHIES over 2^17 x 256 B, device-resident
+    nonces = rnd(n2 * 512)
+    pw2 = rnd(n2 * 32)
+    pw2_off = torch.arange(n2 + 1, dtype=torch.int64, device=dev) * 32
+    m_off = torch.arange(n2 + 1, dtype=torch.int64, device=dev) * mlen
+    ct, pt = torch.empty_like(data), torch.empty_like(data)
+    tag = torch.zeros(n2 * 64, dtype=torch.uint8, device=dev)
+    ok2 = torch.zeros(n2, dtype=torch.uint8, device=dev)
+    ms_e = timed(lambda: eng.sponge_encrypt_dev(pw2, pw2_off, n2 * 32, nonces, 512, data, m_off, 512, ct, tag), 5)
+    ms_d = timed(lambda: eng.sponge_decrypt_dev(pw2, pw2_off, n2 * 32, nonces, 512, ct, m_off, tag, 512, pt, ok2), 5)
+    assert bool(ok2.all().item()) and bool(torch.equal(pt, data)), "sponge AE round trip failed"
+    ae_perms = 6 + 32 + 32  # key derivation (z || pw: 5 key blocks + 1) + tag pass + keystream (2 absorb + 30 squeeze); prefix cached
+    out["sha3_encrypt_2^16x4KB"] = {
+        "encrypt_GBps": world * n2 * mlen / (ms_e * 1e-3) / 1e9, "decrypt_GBps": world * n2 * mlen / (ms_d * 1e-3) / 1e9,
+        "ms_encrypt": ms_e, "ms_decrypt": ms_d,
+        "frac_int_alu_encrypt": n2 * ae_perms * OPS_PER_PERM / (ms_e * 1e-3) / peaks["lop3"], "perms_per_msg": ae_perms}
+    del ct, pt, nonces
+
+    n5 = 1 << 17
+    k_rand = rnd(n5 * 56)
+    m5 = msg[: n5 * 256]
+    m5_off = msg_off[: n5 + 1]
+    ct5, pt5 = torch.empty_like(m5), torch.empty_like(m5)
+    tag5 = torch.zeros(n5 * 56, dtype=torch.uint8, device=dev)
+    zpt = torch.zeros(n5 * 112, dtype=torch.uint8, device=dev)
+    ok5 = torch.zeros(n5, dtype=torch.uint8, device=dev)
+    ms_e = timed(lambda: eng.ed448_key_encrypt_dev(pub, k_rand, m5, m5_off, 512, ct5, tag5, zpt), 2, 1)
+    ms_d = timed(lambda: eng.ed448_key_decrypt_dev(pw, pw_off[: n5 + 1], zpt, ct5, m5_off, tag5, 512, pt5, ok5), 2, 1)
+    assert bool(ok5.all().item()) and bool(torch.equal(pt5, m5)), "ECDHIES round trip failed"
+    out["ed448_ecdhies_2^17x256B"] = {
+        "key_encrypts_per_s": world * n5 / (ms_e * 1e-3), "key_decrypts_per_s": world * n5 / (ms_d * 1e-3),
+        "ms_encrypt": ms_e, "ms_decrypt": ms_d,
+        "note": "encrypt = 1 variable-base + 1 fixed-base scalar mult + 3 KMACs, decrypt = 1 variable-base + 4 KMACs"}
+
+    # e2e for the Ed448 half of the metric: host buffers through capy_ed448_fixed_base_batch (H2D 56 B, D2H 112 B per item)
+    import time as _t
+    n6 = 1 << 18
+    h_sc = eng.pinned(n6 * 56)
+    h_sc[:] = sc[: n6 * 56].cpu().numpy()
+    h_pts = eng.pinned(n6 * 112).reshape(n6, 112)
+    eng.ed448_fixed_base(h_sc, out=h_pts)
+    if dist:
+        dist.barrier()
+    t0 = _t.perf_counter()
+    for _ in range(3):
+        eng.ed448_fixed_base(h_sc, out=h_pts)
+    dt = (_t.perf_counter() - t0) / 3
+    if dist:
+        t = torch.tensor([dt], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    assert h_pts[:1].tobytes() == pts[:112].cpu().numpy().tobytes()
+    out["ed448_fixed_base_e2e_2^18"] = {"scalar_mults_per_s": world * n6 / dt, "ms_per_step": dt * 1e3,
+                                        "h2d_bytes_per_step": n6 * 56, "d2h_bytes_per_step": n6 * 112,
+                                        "api": "capy_ed448_fixed_base_batch (pinned host buffers from capy_host_alloc)"}
     return out
 
 

@@ -1,0 +1,118 @@
+// keccak_pair_probe.cu -- development tool: (1) checks keccak_f1600_pair against keccak_f1600 on the device,
+// (2) times a chain of permutations per thread / per thread pair at one warp per scheduler.
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#include "keccak_pair.cuh"
+using namespace capy;
+
+__global__ void __launch_bounds__(128) chain_single(uint64_t* st, int nperm) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  Lane a[25];
+  for (int k = 0; k < 25; k++) { uint64_t v = st[(size_t)t * 25 + k]; a[k].lo = (uint32_t)v; a[k].hi = (uint32_t)(v >> 32); }
+  for (int p = 0; p < nperm; p++) keccak_f1600(a);
+  for (int k = 0; k < 25; k++) st[(size_t)t * 25 + k] = ((uint64_t)a[k].hi << 32) | a[k].lo;
+}
+__global__ void __launch_bounds__(128) chain_pair(uint64_t* st, int nperm) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int item = t >> 1;
+  const uint32_t half = t & 1;
+  uint32_t h[25];
+  for (int k = 0; k < 25; k++) { uint64_t v = st[(size_t)item * 25 + k]; h[k] = half ? (uint32_t)(v >> 32) : (uint32_t)v; }
+  for (int p = 0; p < nperm; p++) keccak_f1600_pair(h, half);
+  uint32_t* o = reinterpret_cast<uint32_t*>(st);
+  for (int k = 0; k < 25; k++) o[((size_t)item * 25 + k) * 2 + half] = h[k];
+}
+
+// one state per warp: thread l < 25 owns lane l = x + 5y
+__constant__ uint8_t RHO25[25] = {0, 1, 62, 28, 27, 36, 44, 6, 55, 20, 3, 10, 43, 25, 39, 41, 45, 15, 21, 8, 18, 2, 61, 56, 14};
+__global__ void __launch_bounds__(128) chain_warp25(uint64_t* st, int nperm) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int item = t >> 5;
+  const int l = threadIdx.x & 31;
+  const int ll = l < 25 ? l : 0;
+  const int x = ll % 5, y = ll / 5;
+  uint64_t v = st[(size_t)item * 25 + ll];
+  uint32_t lo = (uint32_t)v, hi = (uint32_t)(v >> 32);
+  const int c1 = (ll + 5) % 25, c2 = (ll + 10) % 25, c3 = (ll + 15) % 25, c4 = (ll + 20) % 25;
+  const int xm = (x + 4) % 5 + 5 * y, xp = (x + 1) % 5 + 5 * y;
+  const uint32_t rho = RHO25[ll];
+  const uint32_t swap = rho >= 32, m = rho & 31;
+  // destination (X', Y') = (x, y): B[X'][Y'] comes from lane ((X' + 3Y') % 5) + 5 X'
+  const int s0 = ((x + 3 * y) % 5) + 5 * x;
+  const int s1 = (((x + 1) % 5 + 3 * y) % 5) + 5 * ((x + 1) % 5);
+  const int s2 = (((x + 2) % 5 + 3 * y) % 5) + 5 * ((x + 2) % 5);
+  const uint32_t is0 = ll == 0 && l == 0 ? 0xffffffffu : 0u;
+  const unsigned FULL = 0xffffffffu;
+  for (int p = 0; p < nperm; p++) {
+#pragma unroll 1
+    for (int r = 0; r < 24; r++) {
+      uint32_t clo = lop_xor3(lop_xor3(lo, __shfl_sync(FULL, lo, c1), __shfl_sync(FULL, lo, c2)), __shfl_sync(FULL, lo, c3), __shfl_sync(FULL, lo, c4));
+      uint32_t chi = lop_xor3(lop_xor3(hi, __shfl_sync(FULL, hi, c1), __shfl_sync(FULL, hi, c2)), __shfl_sync(FULL, hi, c3), __shfl_sync(FULL, hi, c4));
+      const uint32_t mlo = __shfl_sync(FULL, clo, xm), mhi = __shfl_sync(FULL, chi, xm);
+      const uint32_t plo = __shfl_sync(FULL, clo, xp), phi = __shfl_sync(FULL, chi, xp);
+      uint32_t tlo = lop_xor3(lo, mlo, __funnelshift_l(phi, plo, 1));
+      uint32_t thi = lop_xor3(hi, mhi, __funnelshift_l(plo, phi, 1));
+      const uint32_t alo = swap ? thi : tlo, ahi = swap ? tlo : thi;
+      const uint32_t elo = __funnelshift_l(ahi, alo, m), ehi = __funnelshift_l(alo, ahi, m);
+      const uint32_t b0l = __shfl_sync(FULL, elo, s0), b0h = __shfl_sync(FULL, ehi, s0);
+      const uint32_t b1l = __shfl_sync(FULL, elo, s1), b1h = __shfl_sync(FULL, ehi, s1);
+      const uint32_t b2l = __shfl_sync(FULL, elo, s2), b2h = __shfl_sync(FULL, ehi, s2);
+      const uint2 rc = KECCAK_RC[r];
+      lo = lop_chi(b0l, b1l, b2l) ^ (rc.x & is0);
+      hi = lop_chi(b0h, b1h, b2h) ^ (rc.y & is0);
+    }
+  }
+  if (l < 25) st[(size_t)item * 25 + l] = ((uint64_t)hi << 32) | lo;
+}
+
+int main(int argc, char** argv) {
+  const int nperm = argc > 1 ? atoi(argv[1]) : 2000;
+  cudaDeviceProp prop; cudaGetDeviceProperties(&prop, 0);
+  const int sms = prop.multiProcessorCount;
+  for (int wps = 1; wps <= 4; wps *= 2) {  // warps per scheduler
+    const int blocks = sms * wps, threads = blocks * 128;
+    std::vector<uint64_t> init((size_t)threads * 25);
+    uint64_t x = 88172645463325252ull;
+    for (auto& v : init) { x ^= x << 13; x ^= x >> 7; x ^= x << 17; v = x; }
+    uint64_t *d1, *d2;
+    cudaMalloc(&d1, init.size() * 8); cudaMalloc(&d2, init.size() * 8);
+    cudaMemcpy(d1, init.data(), init.size() * 8, cudaMemcpyHostToDevice);
+    cudaMemcpy(d2, init.data(), init.size() * 8, cudaMemcpyHostToDevice);
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float ms1, ms2;
+    chain_single<<<blocks, 128>>>(d1, 2); chain_pair<<<blocks, 128>>>(d2, 2);  // warm-up (also part of the check)
+    cudaEventRecord(e0); chain_single<<<blocks, 128>>>(d1, nperm); cudaEventRecord(e1); cudaEventSynchronize(e1);
+    cudaEventElapsedTime(&ms1, e0, e1);
+    cudaEventRecord(e0); chain_pair<<<blocks, 128>>>(d2, nperm); cudaEventRecord(e1); cudaEventSynchronize(e1);
+    cudaEventElapsedTime(&ms2, e0, e1);
+    {
+      uint64_t* d3; cudaMalloc(&d3, init.size() * 8);
+      cudaMemcpy(d3, init.data(), init.size() * 8, cudaMemcpyHostToDevice);
+      chain_warp25<<<blocks, 128>>>(d3, 2);
+      float ms3;
+      cudaEventRecord(e0); chain_warp25<<<blocks, 128>>>(d3, nperm); cudaEventRecord(e1); cudaEventSynchronize(e1);
+      cudaEventElapsedTime(&ms3, e0, e1);
+      std::vector<uint64_t> r3((size_t)threads * 25), r1b((size_t)threads * 25);
+      cudaMemcpy(r3.data(), d3, r3.size() * 8, cudaMemcpyDeviceToHost);
+      cudaMemcpy(r1b.data(), d1, r1b.size() * 8, cudaMemcpyDeviceToHost);
+      size_t bad3 = 0;
+      for (size_t i = 0; i < (size_t)threads / 32 * 25; i++) bad3 += r1b[i] != r3[i];
+      printf("{\"warps_per_scheduler\": %d, \"warp25_us_per_perm\": %.4f, \"chain_speedup_vs_single\": %.3f, \"warp25_Gperm_s\": %.4f, \"mismatching_lanes\": %zu}\n",
+             wps, ms3 * 1e3 / nperm, ms1 / ms3, threads / 32 / (ms3 * 1e-3 / nperm) / 1e9, bad3);
+      cudaFree(d3);
+    }
+    // pair kernel covers threads/2 items: compare those
+    std::vector<uint64_t> r1((size_t)threads * 25), r2((size_t)threads * 25);
+    cudaMemcpy(r1.data(), d1, r1.size() * 8, cudaMemcpyDeviceToHost);
+    cudaMemcpy(r2.data(), d2, r2.size() * 8, cudaMemcpyDeviceToHost);
+    size_t bad = 0;
+    for (size_t i = 0; i < (size_t)threads / 2 * 25; i++) bad += r1[i] != r2[i];
+    printf("{\"warps_per_scheduler\": %d, \"nperm\": %d, \"single_us_per_perm\": %.4f, \"pair_us_per_perm\": %.4f, "
+           "\"chain_speedup\": %.3f, \"single_Gperm_s\": %.3f, \"pair_Gperm_s\": %.3f, \"mismatching_lanes\": %zu, \"err\": \"%s\"}\n",
+           wps, nperm, ms1 * 1e3 / nperm, ms2 * 1e3 / nperm, ms1 / ms2, threads / (ms1 * 1e-3 / nperm) / 1e9,
+           threads / 2 / (ms2 * 1e-3 / nperm) / 1e9, bad, cudaGetErrorString(cudaGetLastError()));
+    cudaFree(d1); cudaFree(d2);
+  }
+  return 0;
+}

@@ -141,10 +141,11 @@ class Engine:
                                                  _hp(cs_a), len(cs_a), out_bits, oo, _hp(out)))
         return out
 
-    def ed448_fixed_base(self, scalars_be56) -> np.ndarray:
+    def ed448_fixed_base(self, scalars_be56, out: np.ndarray | None = None) -> np.ndarray:
         sc = _u8(scalars_be56)
         n = len(sc) // 56
-        out = np.zeros((n, 112), dtype=np.uint8)
+        if out is None:
+            out = np.zeros((n, 112), dtype=np.uint8)
         self._check(self.lib.capy_ed448_fixed_base_batch(self._ctx, _hp(sc), n, _hp(out)))
         return out
 
