@@ -6,7 +6,7 @@ use std::{env, path::PathBuf, process::Command};
 fn main() {
     let out = PathBuf::from(env::var("OUT_DIR").unwrap());
     let nvcc = env::var("NVCC").unwrap_or_else(|_| "nvcc".into());
-    let srcs = ["ctx.cu", "sha3_api.cu", "ed448_api.cu", "ed448_fixed.cu", "ed448_var.cu"];
+    let srcs = ["ctx.cu", "sha3_api.cu", "ed448_api.cu", "ed448_fixed.cu", "ed448_var.cu", "ae_api.cu"];
     let mut objs = vec![];
     for s in srcs {
         let obj = out.join(s.replace(".cu", ".o"));

@@ -30,6 +30,29 @@ extern "C" {
                              msgs: *const u8, msg_off: *const u64, n: u64, h56: *mut u8, z_be56: *mut u8) -> c_int;
     fn capy_ed448_verify_batch(ctx: *mut CapyCtx, d_bits: c_int, pub_xy112: *const u8, msgs: *const u8,
                                msg_off: *const u64, h56: *const u8, z_be56: *const u8, n: u64, ok: *mut u8) -> c_int;
+    fn capy_sponge_encrypt_batch(ctx: *mut CapyCtx, d_bits: c_int, variant: c_int, pws: *const u8, pw_off: *const u64,
+                                 nonces: *const u8, nonce_len: u64, msgs: *const u8, msg_off: *const u64, n: u64,
+                                 ct: *mut u8, tag64: *mut u8) -> c_int;
+    fn capy_sponge_decrypt_batch(ctx: *mut CapyCtx, d_bits: c_int, variant: c_int, pws: *const u8, pw_off: *const u64,
+                                 nonces: *const u8, nonce_len: u64, ct: *const u8, ct_off: *const u64,
+                                 tag64: *const u8, n: u64, out: *mut u8, ok: *mut u8) -> c_int;
+    fn capy_ed448_key_encrypt_batch(ctx: *mut CapyCtx, d_bits: c_int, pub_xy112: *const u8, k_rand56: *const u8,
+                                    msgs: *const u8, msg_off: *const u64, n: u64, ct: *mut u8, tag56: *mut u8,
+                                    z_xy112: *mut u8) -> c_int;
+    fn capy_ed448_key_decrypt_batch(ctx: *mut CapyCtx, d_bits: c_int, pws: *const u8, pw_off: *const u64,
+                                    z_xy112: *const u8, ct: *const u8, ct_off: *const u64, tag56: *const u8, n: u64,
+                                    out: *mut u8, ok: *mut u8) -> c_int;
+}
+
+const CAPY_AE_SHA3: c_int = 0;
+
+/// affine (x || y, 2 x 56 little-endian bytes) of an `ExtendedPoint` -- the point format of the C ABI
+fn point_to_xy(p: &ExtendedPoint) -> [u8; 112] {
+    let a = p.to_affine();
+    let mut o = [0u8; 112];
+    o[..56].copy_from_slice(&a.x.to_bytes());
+    o[56..].copy_from_slice(&a.y.to_bytes());
+    o
 }
 
 /// One engine context (one or more GPUs).  Calls are blocking and serialised per context.
@@ -138,13 +161,172 @@ impl Gpu {
         Ok(())
     }
 
-    /// Batched `Signable::verify`; `pub_xy[i]` is the affine public key (x || y, little-endian).
-    pub fn verify(&self, msgs: &[Message], pub_xy: &[[u8; 112]]) -> Vec<Result<(), OperationError>> {
-        // group by security parameter, call capy_ed448_verify_batch, map ok[i] == 0 to
-        // Err(SignatureVerificationFailure); missing sig / d map to SignatureNotSet / SecurityParameterNotSet
-        // exactly as src/ecc/signable.rs:73-74.  (Body elided: same shape as `sign`.)
-        let _ = (msgs, pub_xy, capy_ed448_verify_batch as usize);
-        unimplemented!("see capycrypt_b200/host/capycrypt_gpu.hpp::Engine::verify for the complete logic")
+    /// Batched `Signable::verify`; `pub_keys[i]` verifies `msgs[i]`.  Same errors as src/ecc/signable.rs:72-86.
+    pub fn verify(&self, msgs: &[Message], pub_keys: &[ExtendedPoint]) -> Vec<Result<(), OperationError>> {
+        let mut res: Vec<Result<(), OperationError>> = msgs.iter().map(|_| Ok(())).collect();
+        for d in [SecParam::D224, SecParam::D256, SecParam::D384, SecParam::D512] {
+            let mut idx = Vec::new();
+            for (i, m) in msgs.iter().enumerate() {
+                if m.sig.is_none() {
+                    res[i] = Err(OperationError::SignatureNotSet);
+                } else if m.d.is_none() {
+                    res[i] = Err(OperationError::SecurityParameterNotSet);
+                } else if m.d == Some(d) {
+                    idx.push(i);
+                }
+            }
+            if idx.is_empty() {
+                continue;
+            }
+            let (md, mo) = pack(idx.iter().map(|&i| msgs[i].msg.as_slice()));
+            let (mut pk, mut h, mut z) = (Vec::new(), Vec::new(), Vec::new());
+            for &i in &idx {
+                let sig = msgs[i].sig.as_ref().unwrap();
+                pk.extend_from_slice(&point_to_xy(&pub_keys[i]));
+                h.extend_from_slice(&sig.h);
+                z.extend_from_slice(&sig.z.val.to_be_bytes());
+            }
+            let mut ok = vec![0u8; idx.len()];
+            let rc = unsafe {
+                capy_ed448_verify_batch(self.ctx, d as c_int, pk.as_ptr(), md.as_ptr(), mo.as_ptr(), h.as_ptr(), z.as_ptr(),
+                                        idx.len() as u64, ok.as_mut_ptr())
+            };
+            for (k, &i) in idx.iter().enumerate() {
+                if (rc != 0 && rc != -4) || ok[k] == 0 {
+                    res[i] = Err(OperationError::SignatureVerificationFailure);
+                }
+            }
+        }
+        res
+    }
+
+    /// Batched `SpongeEncryptable::sha3_encrypt` (src/sha3/encryptable.rs:29-45).  The 512 random nonce bytes per
+    /// message are drawn here with the reference's own `get_random_bytes` (the C ABI has no RNG).
+    pub fn sha3_encrypt(&self, msgs: &mut [Message], pws: &[&[u8]], d: SecParam) -> Result<(), OperationError> {
+        use crate::sha3::aux_functions::byte_utils::get_random_bytes;
+        let n = msgs.len();
+        let nonces: Vec<Vec<u8>> = (0..n).map(|_| get_random_bytes(512)).collect();
+        let z: Vec<u8> = nonces.iter().flatten().copied().collect();
+        let (pd, po) = pack(pws.iter().copied());
+        let (md, mo) = pack(msgs.iter().map(|m| m.msg.as_slice()));
+        let (mut ct, mut tag) = (vec![0u8; md.len()], vec![0u8; n * 64]);
+        status(unsafe {
+            capy_sponge_encrypt_batch(self.ctx, d as c_int, CAPY_AE_SHA3, pd.as_ptr(), po.as_ptr(), z.as_ptr(), 512,
+                                      md.as_ptr(), mo.as_ptr(), n as u64, ct.as_mut_ptr(), tag.as_mut_ptr())
+        })?;
+        for (i, (m, nonce)) in msgs.iter_mut().zip(nonces).enumerate() {
+            m.msg = Box::new(ct[mo[i] as usize..mo[i + 1] as usize].to_vec());
+            m.digest = tag[64 * i..64 * i + 64].to_vec();
+            m.sym_nonce = Some(nonce);
+            m.d = Some(d);
+        }
+        Ok(())
+    }
+
+    /// Batched `SpongeEncryptable::sha3_decrypt` (:58-83): on `SHA3DecryptionFailure` the message keeps its ciphertext.
+    pub fn sha3_decrypt(&self, msgs: &mut [Message], pws: &[&[u8]]) -> Vec<Result<(), OperationError>> {
+        let mut res: Vec<Result<(), OperationError>> = msgs.iter().map(|_| Ok(())).collect();
+        for d in [SecParam::D224, SecParam::D256, SecParam::D384, SecParam::D512] {
+            let mut idx = Vec::new();
+            for (i, m) in msgs.iter().enumerate() {
+                if m.d.is_none() {
+                    res[i] = Err(OperationError::SecurityParameterNotSet);
+                } else if m.sym_nonce.is_none() {
+                    res[i] = Err(OperationError::SymNonceNotSet);
+                } else if m.d == Some(d) {
+                    idx.push(i);
+                }
+            }
+            if idx.is_empty() {
+                continue;
+            }
+            let (pd, po) = pack(idx.iter().map(|&i| pws[i]));
+            let (cd, co) = pack(idx.iter().map(|&i| msgs[i].msg.as_slice()));
+            let z: Vec<u8> = idx.iter().flat_map(|&i| msgs[i].sym_nonce.as_ref().unwrap().iter().copied()).collect();
+            let mut tags = vec![0u8; idx.len() * 64];
+            for (k, &i) in idx.iter().enumerate() {
+                let t = &msgs[i].digest;
+                tags[64 * k..64 * k + t.len().min(64)].copy_from_slice(&t[..t.len().min(64)]);
+            }
+            let (mut out, mut ok) = (vec![0u8; cd.len()], vec![0u8; idx.len()]);
+            let rc = unsafe {
+                capy_sponge_decrypt_batch(self.ctx, d as c_int, CAPY_AE_SHA3, pd.as_ptr(), po.as_ptr(), z.as_ptr(), 512,
+                                          cd.as_ptr(), co.as_ptr(), tags.as_ptr(), idx.len() as u64, out.as_mut_ptr(),
+                                          ok.as_mut_ptr())
+            };
+            for (k, &i) in idx.iter().enumerate() {
+                if rc == 0 && ok[k] == 1 && msgs[i].digest.len() == 64 {
+                    msgs[i].msg = Box::new(out[co[k] as usize..co[k + 1] as usize].to_vec());
+                } else {
+                    res[i] = Err(OperationError::SHA3DecryptionFailure);
+                }
+            }
+        }
+        res
+    }
+
+    /// Batched `KeyEncryptable::key_encrypt` (src/ecc/encryptable.rs:34-50); `pub_keys[i]` encrypts `msgs[i]`.
+    pub fn key_encrypt(&self, msgs: &mut [Message], pub_keys: &[ExtendedPoint], d: SecParam) -> Result<(), OperationError> {
+        use crate::sha3::aux_functions::byte_utils::get_random_bytes;
+        use tiny_ed448_goldilocks::curve::affine::AffinePoint;
+        let n = msgs.len();
+        let k_rand: Vec<u8> = (0..n).flat_map(|_| get_random_bytes(56)).collect();
+        let pk: Vec<u8> = pub_keys.iter().flat_map(|p| point_to_xy(p)).collect();
+        let (md, mo) = pack(msgs.iter().map(|m| m.msg.as_slice()));
+        let (mut ct, mut tag, mut z) = (vec![0u8; md.len()], vec![0u8; n * 56], vec![0u8; n * 112]);
+        status(unsafe {
+            capy_ed448_key_encrypt_batch(self.ctx, d as c_int, pk.as_ptr(), k_rand.as_ptr(), md.as_ptr(), mo.as_ptr(),
+                                         n as u64, ct.as_mut_ptr(), tag.as_mut_ptr(), z.as_mut_ptr())
+        })?;
+        for (i, m) in msgs.iter_mut().enumerate() {
+            m.msg = Box::new(ct[mo[i] as usize..mo[i + 1] as usize].to_vec());
+            m.digest = tag[56 * i..56 * i + 56].to_vec();
+            // field decoding is crate-specific: FieldElement::from_bytes on the two 56-byte halves
+            m.asym_nonce = Some(AffinePoint::from_xy_bytes(&z[112 * i..112 * i + 112]).to_extended());
+            m.d = Some(d);
+        }
+        Ok(())
+    }
+
+    /// Batched `KeyEncryptable::key_decrypt` (:72-94): on `KeyDecryptionError` the message keeps its ciphertext.
+    pub fn key_decrypt(&self, msgs: &mut [Message], pws: &[&[u8]]) -> Vec<Result<(), OperationError>> {
+        let mut res: Vec<Result<(), OperationError>> = msgs.iter().map(|_| Ok(())).collect();
+        for d in [SecParam::D224, SecParam::D256, SecParam::D384, SecParam::D512] {
+            let mut idx = Vec::new();
+            for (i, m) in msgs.iter().enumerate() {
+                if m.asym_nonce.is_none() {
+                    res[i] = Err(OperationError::SymNonceNotSet); // sic: ecc/encryptable.rs:73
+                } else if m.d.is_none() {
+                    res[i] = Err(OperationError::SecurityParameterNotSet);
+                } else if m.d == Some(d) {
+                    idx.push(i);
+                }
+            }
+            if idx.is_empty() {
+                continue;
+            }
+            let (pd, po) = pack(idx.iter().map(|&i| pws[i]));
+            let (cd, co) = pack(idx.iter().map(|&i| msgs[i].msg.as_slice()));
+            let z: Vec<u8> = idx.iter().flat_map(|&i| point_to_xy(msgs[i].asym_nonce.as_ref().unwrap())).collect();
+            let mut tags = vec![0u8; idx.len() * 56];
+            for (k, &i) in idx.iter().enumerate() {
+                let t = &msgs[i].digest;
+                tags[56 * k..56 * k + t.len().min(56)].copy_from_slice(&t[..t.len().min(56)]);
+            }
+            let (mut out, mut ok) = (vec![0u8; cd.len()], vec![0u8; idx.len()]);
+            let rc = unsafe {
+                capy_ed448_key_decrypt_batch(self.ctx, d as c_int, pd.as_ptr(), po.as_ptr(), z.as_ptr(), cd.as_ptr(),
+                                             co.as_ptr(), tags.as_ptr(), idx.len() as u64, out.as_mut_ptr(), ok.as_mut_ptr())
+            };
+            for (k, &i) in idx.iter().enumerate() {
+                if (rc == 0 || rc == -4) && ok[k] == 1 && msgs[i].digest.len() == 56 {
+                    msgs[i].msg = Box::new(out[co[k] as usize..co[k + 1] as usize].to_vec());
+                } else {
+                    res[i] = Err(OperationError::KeyDecryptionError);
+                }
+            }
+        }
+        res
     }
 }
 
@@ -153,6 +335,3 @@ impl Drop for Gpu {
         unsafe { capy_gpu_destroy(self.ctx) }
     }
 }
-
-#[allow(dead_code)]
-fn _unused(_: ExtendedPoint, _: *mut c_void) {}
