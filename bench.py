@@ -402,6 +402,9 @@ def extras(eng, dev, peaks, world, dist, rank):
     t_off5 = torch.from_numpy(off5).to(dev)
     o5 = torch.zeros(len(lens) * 64, dtype=torch.uint8, device=dev)
     ms = timed(lambda: eng.sha3_dev(d5, t_off5, 512, o5), 2, 1)
+    # A/B: the same batch with one thread per message everywhere (CAPY_FLAG_NO_PAIR = 2)
+    ms_solo = timed(lambda: eng._check(eng.lib.capy_sha3_batch_dev(eng._ctx, 0, eng._stream(), 512, d5.data_ptr(),
+                                                                   t_off5.data_ptr(), len(lens), o5.data_ptr(), 2)), 1, 1)
     perms5 = int(((lens + 1 + 71) // 72).sum())
     tot_bytes = torch.tensor([float(nbytes5)], device=dev, dtype=torch.float64)
     tot_perms = torch.tensor([float(perms5)], device=dev, dtype=torch.float64)
@@ -412,8 +415,10 @@ def extras(eng, dev, peaks, world, dist, rank):
         "GBps": float(tot_bytes.item()) / (ms * 1e-3) / 1e9, "ms_per_step": ms, "msgs_this_rank": int(len(lens)),
         "frac_int_alu": float(tot_perms.item()) / world * OPS_PER_PERM / (ms * 1e-3) / peaks["lop3"],
         "scaling": "strong", "longest_chain_perms": int((lens.max() + 1 + 71) // 72),
+        "ms_one_thread_per_message": ms_solo,
         "note": "a sponge is sequential per message: the step cannot be shorter than the longest message's chain "
-                "(1 MiB = 14 564 permutations ~ 71 ms on one scheduler)"}
+                "(1 MiB = 14 564 permutations: 67 ms with one thread per message, ~57 ms with the two-thread tier "
+                "the longest messages of a chain-bound batch run in)"}
     del d5, o5, t_off5
 
     # cfg 3: Ed448 fixed-base [s]G for 2^20 scalars

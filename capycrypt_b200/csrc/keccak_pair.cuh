@@ -27,17 +27,18 @@ __device__ __forceinline__ uint32_t rot_half(uint32_t own, uint32_t partner) {
   {                                                                                                \
     const uint32_t t = lop_xor3(h[(X) + 5 * (Y)], c[((X) + 4) % 5], r1[((X) + 1) % 5]);            \
     uint32_t p = 0;                                                                                \
-    if ((R) != 0) p = __shfl_xor_sync(0xffffffffu, t, 1);                                          \
+    if ((R) != 0) p = __shfl_xor_sync(mask, t, 1);                                                 \
     b[(Y) + 5 * ((2 * (X) + 3 * (Y)) % 5)] = rot_half<(R)>(t, p);                                  \
   }
 
-// rc_half = this thread's half of the round constant
-__device__ __forceinline__ void keccak_round_pair(uint32_t (&h)[25], uint32_t rc_half) {
+// rc_half = this thread's half of the round constant; mask = the two lanes of the pair (pairs of one warp may
+// sit in different loop iterations, so every shuffle names only its own pair)
+__device__ __forceinline__ void keccak_round_pair(uint32_t (&h)[25], uint32_t rc_half, unsigned mask) {
   uint32_t c[5], r1[5], b[25];
 #pragma unroll
   for (int x = 0; x < 5; x++) c[x] = lop_xor3(lop_xor3(h[x], h[x + 5], h[x + 10]), h[x + 15], h[x + 20]);
 #pragma unroll
-  for (int x = 0; x < 5; x++) r1[x] = rot_half<1>(c[x], __shfl_xor_sync(0xffffffffu, c[x], 1));
+  for (int x = 0; x < 5; x++) r1[x] = rot_half<1>(c[x], __shfl_xor_sync(mask, c[x], 1));
   CAPY_PAIR_RHO_PI(0, 0, 0)  CAPY_PAIR_RHO_PI(1, 0, 1)  CAPY_PAIR_RHO_PI(2, 0, 62) CAPY_PAIR_RHO_PI(3, 0, 28) CAPY_PAIR_RHO_PI(4, 0, 27)
   CAPY_PAIR_RHO_PI(0, 1, 36) CAPY_PAIR_RHO_PI(1, 1, 44) CAPY_PAIR_RHO_PI(2, 1, 6)  CAPY_PAIR_RHO_PI(3, 1, 55) CAPY_PAIR_RHO_PI(4, 1, 20)
   CAPY_PAIR_RHO_PI(0, 2, 3)  CAPY_PAIR_RHO_PI(1, 2, 10) CAPY_PAIR_RHO_PI(2, 2, 43) CAPY_PAIR_RHO_PI(3, 2, 25) CAPY_PAIR_RHO_PI(4, 2, 39)
@@ -52,12 +53,12 @@ __device__ __forceinline__ void keccak_round_pair(uint32_t (&h)[25], uint32_t rc
 }
 #undef CAPY_PAIR_RHO_PI
 
-// all 32 lanes of the warp must call this together (full-mask shuffles)
-__device__ __forceinline__ void keccak_f1600_pair(uint32_t (&h)[25], uint32_t half) {
+// both threads of the pair must call this together
+__device__ __forceinline__ void keccak_f1600_pair(uint32_t (&h)[25], uint32_t half, unsigned mask = 0xffffffffu) {
 #pragma unroll 1
   for (int r = 0; r < 24; r++) {
     const uint2 rc = KECCAK_RC[r];
-    keccak_round_pair(h, half ? rc.y : rc.x);
+    keccak_round_pair(h, half ? rc.y : rc.x, mask);
   }
 }
 

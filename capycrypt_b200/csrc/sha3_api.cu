@@ -222,14 +222,21 @@ __global__ void len_scatter_kernel(const uint64_t* __restrict__ off, uint64_t n,
 
 struct LaunchPlan {
   const uint32_t* order = nullptr;
-  int warps_per_smsp = 0;  // 0 = unthrottled
+  int warps_per_smsp = 0;   // 0 = unthrottled
+  uint64_t pair_items = 0;  // ranks [0, pair_items) run two threads per item (sponge_pair_kernel)
 };
 
-// builds the descending-length order for a ragged batch; decides the occupancy throttle
+// Measured on B200 at one warp per scheduler: a thread-per-state chain advances one permutation per 4.55 us, a
+// thread pair one per 3.35 us in isolation (csrc/keccak_pair_probe.cu) and per 3.7-3.95 us inside the sponge
+// (absorb loads, warp-uniform step loop; 1 024 x 1 MiB SHA3-512: 53.6 ms against 67.0 ms).
+constexpr double kPairChainRatio = 3.95 / 4.6;
+
+// builds the descending-length order for a ragged batch; decides the occupancy throttle and how many of the
+// longest items go to the two-threads-per-item kernel
 static int plan_ragged(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t st, const uint64_t* d_off, uint64_t n,
-                       uint32_t stride_bytes, LaunchPlan* plan) {
+                       uint32_t stride_bytes, LaunchPlan* plan, bool allow_pair = true) {
   *plan = LaunchPlan();
-  if (n < 2 || n > 0xffffffffull) return CAPY_OK;
+  if (n < 1 || n > 0xffffffffull) return CAPY_OK;
   int si = 0;  // scratch pair per internal stream (chunks on different streams overlap); callers' streams use pair 0
   for (int k = 0; k < kNumStreams; k++)
     if (dc.streams[k] == st) si = k;
@@ -246,14 +253,29 @@ static int plan_ragged(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t st, const uint
   CAPY_CUDA(ctx, cudaStreamSynchronize(st));
   const uint64_t total_blocks = (uint64_t)h_sum[0] | ((uint64_t)h_sum[1] << 32);
   const uint32_t max_blocks = h_sum[2] + 1, bins = h_sum[3];
+  // time in units of one thread-per-state permutation on one scheduler: all work spread over every scheduler
+  // (32 states per warp, one warp per scheduler) vs the longest chain
+  const double ideal = (double)total_blocks / (32.0 * 4.0 * dc.sm_count);
+  // Chain-bound batch: every item whose own chain would outlast the work-bound time goes to the pair kernel,
+  // which occupies whole SMs (64 items each) next to the thread-per-item kernel.  At most half of the SMs.
+  const uint64_t pair_cap = 64ull * (uint64_t)(dc.sm_count / 2);
+  if (allow_pair && max_blocks > 64 && (double)max_blocks > 1.05 * ideal) {
+    const double target = std::max(1.03 * ideal, kPairChainRatio * (double)max_blocks);
+    uint64_t need = n;
+    if (bins > 1 && target < (double)max_blocks) {
+      const uint32_t tb = std::min<uint32_t>((uint32_t)target, kLenBins - 1);
+      uint32_t above = 0;  // after the scan hist[k] = number of items in bins > k
+      CAPY_CUDA(ctx, cudaMemcpyAsync(&above, hist + tb, sizeof above, cudaMemcpyDeviceToHost, st));
+      CAPY_CUDA(ctx, cudaStreamSynchronize(st));
+      need = above;
+    }
+    plan->pair_items = std::min<uint64_t>(std::min<uint64_t>((need + 63) / 64 * 64, pair_cap), n);
+  }
   if (bins <= 1) return CAPY_OK;  // uniform lengths: nothing to order
   len_scatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_off, n, stride_bytes, hist, order);
   ctx->launches++;
   CAPY_CUDA(ctx, cudaGetLastError());
   plan->order = order;
-  // time in units of one warp-permutation on one scheduler: all work spread over every scheduler vs the
-  // longest chain at w warps per scheduler
-  const double ideal = (double)total_blocks / (32.0 * 4.0 * dc.sm_count);
   plan->warps_per_smsp = 0;
   if ((double)max_blocks * 4.0 > 0.7 * ideal) {
     plan->warps_per_smsp = 3;
@@ -264,7 +286,19 @@ static int plan_ragged(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t st, const uint
 }
 
 template <int LANES>
-static int launch_sponge_t(capy_ctx* ctx, cudaStream_t stream, const SpongeJob& J, unsigned block, int warps_per_smsp) {
+static int launch_sponge_t(capy_ctx* ctx, cudaStream_t stream, SpongeJob J, unsigned block, int warps_per_smsp,
+                           uint64_t pair_items) {
+  if (pair_items) {
+    // chain-bound batch: pair blocks first, then thread-per-item blocks, one block per SM
+    const unsigned pair_blocks = grid_for(2 * pair_items, 128);
+    const unsigned solo_blocks = grid_for(J.n - pair_items, 128);
+    J.first = pair_items;
+    CAPY_CUDA(ctx, cudaFuncSetAttribute(sponge_tiered_kernel<LANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    sponge_tiered_kernel<LANES><<<pair_blocks + solo_blocks, 128, 226 * 1024, stream>>>(J, pair_blocks);
+    ctx->launches++;
+    CAPY_CUDA(ctx, cudaGetLastError());
+    return CAPY_OK;
+  }
   size_t smem = 0;
   if (warps_per_smsp >= 1 && warps_per_smsp <= 3) {
     // one 128-thread block = one warp per scheduler; W blocks per SM via the shared-memory footprint
@@ -299,16 +333,18 @@ static unsigned pick_block(uint64_t n, int sm_count, int threads_per_sm) {
 }
 
 static int launch_sponge(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t stream, int lanes, const SpongeJob& J,
-                         int warps_per_smsp = 0) {
+                         const LaunchPlan& plan = LaunchPlan()) {
   if (J.n == 0) return CAPY_OK;
   const unsigned block = pick_block(J.n, dc.sm_count, 384);
+  const int w = plan.warps_per_smsp;
+  const uint64_t pi = plan.pair_items;
   switch (lanes) {
-    case 9: return launch_sponge_t<9>(ctx, stream, J, block, warps_per_smsp);
-    case 13: return launch_sponge_t<13>(ctx, stream, J, block, warps_per_smsp);
-    case 17: return launch_sponge_t<17>(ctx, stream, J, block, warps_per_smsp);
-    case 18: return launch_sponge_t<18>(ctx, stream, J, block, warps_per_smsp);
-    case 19: return launch_sponge_t<19>(ctx, stream, J, block, warps_per_smsp);
-    case 21: return launch_sponge_t<21>(ctx, stream, J, block, warps_per_smsp);
+    case 9: return launch_sponge_t<9>(ctx, stream, J, block, w, pi);
+    case 13: return launch_sponge_t<13>(ctx, stream, J, block, w, pi);
+    case 17: return launch_sponge_t<17>(ctx, stream, J, block, w, pi);
+    case 18: return launch_sponge_t<18>(ctx, stream, J, block, w, pi);
+    case 19: return launch_sponge_t<19>(ctx, stream, J, block, w, pi);
+    case 21: return launch_sponge_t<21>(ctx, stream, J, block, w, pi);
     default: return CAPY_ERR_BAD_ARG;
   }
 }
@@ -367,11 +403,11 @@ static int launch_sha3(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t stream, int d,
   J.n = n;
   LaunchPlan plan;
   if (off && !(flags & CAPY_FLAG_NO_SORT)) {
-    int rc = plan_ragged(ctx, dc, stream, off, n, rate, &plan);
+    int rc = plan_ragged(ctx, dc, stream, off, n, rate, &plan, !(flags & CAPY_FLAG_NO_PAIR));
     if (rc) return rc;
   }
   J.order = plan.order;
-  return launch_sponge(ctx, dc, stream, lanes, J, plan.warps_per_smsp);
+  return launch_sponge(ctx, dc, stream, lanes, J, plan);
 }
 
 // ---- cSHAKE / KMAC prefix -----------------------------------------------------------------------
@@ -471,7 +507,7 @@ static int launch_cshake(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t stream, int 
     if (rc) return rc;
   }
   J.order = plan.order;
-  return launch_sponge(ctx, dc, stream, (int)(bytepad_value(d) * 8 / 64), J, plan.warps_per_smsp);
+  return launch_sponge(ctx, dc, stream, (int)(bytepad_value(d) * 8 / 64), J, plan);
 }
 
 int launch_kmac_xof(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t stream, const KmacDevArgs& a) {
@@ -510,7 +546,7 @@ int launch_kmac_xof(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t stream, const Kma
     if (rc) return rc;
   }
   J.order = plan.order;
-  return launch_sponge(ctx, dc, stream, (int)(bytepad_value(a.d_bits) * 8 / 64), J, plan.warps_per_smsp);
+  return launch_sponge(ctx, dc, stream, (int)(bytepad_value(a.d_bits) * 8 / 64), J, plan);
 }
 
 }  // namespace capy

@@ -14,6 +14,7 @@
 // trailing permutation (quirk Q8).
 #pragma once
 #include "keccak.cuh"
+#include "keccak_pair.cuh"
 
 #ifndef CAPY_SPONGE_MINB
 #define CAPY_SPONGE_MINB 3
@@ -62,8 +63,10 @@ struct SpongeJob {
   // (c = m ^ kmac_xof(ke, "", |m|, ...), sha3/encryptable.rs:41-42, ecc/encryptable.rs:45)
   const uint8_t* xor_in;
   uint64_t n;
-  // optional permutation of work: item index = order ? order[t] : t (length-sorted launch)
+  // optional permutation of work: item index = order ? order[r] : r for rank r (length-sorted launch)
   const uint32_t* order;
+  // ranks [0, first) belong to sponge_pair_kernel (two threads per item), [first, n) to sponge_kernel
+  uint64_t first;
 };
 
 __device__ __forceinline__ uint32_t left_encode_nbytes(uint64_t v) {
@@ -72,79 +75,136 @@ __device__ __forceinline__ uint32_t left_encode_nbytes(uint64_t v) {
   return nb;
 }
 
-// byte p of bytepad(encode_string(K), w) before zero padding (aux_functions.rs:11-49)
-__device__ __forceinline__ uint32_t key_block_byte(uint64_t p, const uint8_t* key, uint64_t klen, uint32_t w,
-                                                   uint32_t w_nb, uint32_t k_nb) {
-  // left_encode(w)
-  if (p == 0) return w_nb;
-  if (p <= w_nb) return (w >> (8 * (w_nb - p))) & 0xFF;
-  p -= 1 + w_nb;
-  // left_encode(8 * klen)
-  uint64_t bits = klen * 8;
-  if (p == 0) return k_nb;
-  if (p <= k_nb) return (uint32_t)(bits >> (8 * (k_nb - p))) & 0xFF;
-  p -= 1 + k_nb;
-  if (p < klen) return key[p];
-  return 0;
-}
+// ---- per-item geometry of the virtual stream  P | KB | X | T | pad --------------------------------------
+struct SpongeGeom {
+  const uint8_t* prefix;
+  uint32_t prefix_len;
+  const uint8_t* key;  // nullptr = no key block
+  const uint8_t* x;
+  uint32_t trailer, hdr_len;
+  uint64_t k0, k1;      // key bytes
+  uint64_t x0, x1;      // message bytes
+  uint64_t t1;          // end of the trailer
+  uint64_t p1;          // end of the first pad (quirk Q4 only, else == t1)
+  uint64_t padded;      // end of the stream
+  uint64_t nblocks;
+  bool has_pad1, has_pad;
+  uint8_t hdr[12];  // left_encode(w) || left_encode(8 * klen): the head of bytepad(encode_string(K), w)
 
+  __device__ __forceinline__ void init(const SpongeJob& J, uint64_t i) {
+    prefix = J.prefix;
+    prefix_len = J.prefix_len;
+    key = nullptr;
+    uint64_t klen = 0, kb_len = 0;
+    hdr_len = 0;
+    if (J.keys) {
+      if (J.key_off) {
+        key = J.keys + J.key_off[i];
+        klen = J.key_off[i + 1] - J.key_off[i];
+      } else {
+        key = J.keys + i * J.key_stride;
+        klen = J.key_len;
+      }
+      const uint32_t w_nb = left_encode_nbytes(J.w), k_nb = left_encode_nbytes(klen * 8);
+      const uint64_t content = (uint64_t)(1 + w_nb) + (1 + k_nb) + klen;
+      kb_len = (content / J.w + 1) * J.w;  // byte_pad always appends w - len % w zeros (quirk Q3)
+      hdr[hdr_len++] = (uint8_t)w_nb;      // aux_functions.rs:11-49
+      for (uint32_t q = w_nb; q-- > 0;) hdr[hdr_len++] = (uint8_t)(J.w >> (8 * q));
+      hdr[hdr_len++] = (uint8_t)k_nb;
+      const uint64_t bits = klen * 8;
+      for (uint32_t q = k_nb; q-- > 0;) hdr[hdr_len++] = (uint8_t)(bits >> (8 * q));
+    }
+    uint64_t xlen;
+    if (J.off) {
+      x = J.data + J.off[i];
+      xlen = J.off[i + 1] - J.off[i];
+    } else {
+      x = J.data + i * J.msg_stride;
+      xlen = J.msg_len;
+    }
+    trailer = J.trailer;
+    if (J.sha3_suffix) trailer = (xlen % 136u == 135u) ? 0x86u : 0x06u;
+    k0 = (uint64_t)J.prefix_len + hdr_len;
+    k1 = k0 + klen;
+    x0 = (uint64_t)J.prefix_len + kb_len;
+    x1 = x0 + xlen;
+    uint32_t trailer_len = J.trailer_len;
+    if (J.q4_rate) {  // shake_functions.rs:59-61 -> :25-29 on the buffer P|X|04
+      trailer |= (((x1 + 1) % 136u == 135u) ? 0x86u : 0x06u) << 8;
+      trailer_len = 2;
+    }
+    t1 = x1 + trailer_len;
+    // first pad (Q4 only): to a multiple of the SHA3-d rate, only when unaligned
+    p1 = t1;
+    has_pad1 = false;
+    if (J.q4_rate) {
+      const uint64_t rem1 = t1 % J.q4_rate;
+      has_pad1 = rem1 != 0;
+      if (has_pad1) p1 = t1 + (J.q4_rate - rem1);
+    }
+    const uint64_t rem = p1 % J.rate;
+    padded = rem ? p1 + (J.rate - rem) : p1;  // Q1: no pad block when aligned
+    nblocks = padded / J.rate;
+    has_pad = rem != 0;
+    if (J.fips_pad && !has_pad) trailer |= 0x80u << (8 * (trailer_len - 1));
+  }
+
+  // bytes of the segment [seg0, seg1) (stream offsets; base[0] sits at seg0) that fall into the lane at o
+  static __device__ __forceinline__ uint64_t piece(const uint8_t* base, uint64_t seg0, uint64_t seg1, uint64_t o) {
+    const uint64_t lo = o > seg0 ? o : seg0, hi = o + 8 < seg1 ? o + 8 : seg1;
+    uint64_t v = 0;
+#pragma unroll 1
+    for (uint64_t q = lo; q < hi; q++) v |= (uint64_t)base[q - seg0] << (8 * (uint32_t)(q - o));
+    return v;
+  }
+
+  // The 8-byte lane at stream offset o of a boundary block: the OR of the pieces of the (at most five) segments
+  // that overlap it, each piece fetched with a loop over just its own bytes; lanes wholly inside X, inside zero
+  // padding or past the end take one compare each.  (The first version walked all 8 bytes of every lane through
+  // a compare chain: ~2 700 instructions per block against ~700 now; KMAC over 4 KB has two such blocks in 33.)
+  __device__ __forceinline__ uint64_t lane(uint64_t o) const {
+    uint64_t v = 0;
+    if (o >= x0 && o + 8 <= x1) {
+      const uint8_t* p = x + (o - x0);
+#pragma unroll
+      for (int k = 0; k < 8; k++) v |= (uint64_t)p[k] << (8 * k);
+    } else if (o < padded && !(o >= k1 && o + 8 <= x0) && !(o >= t1 && o + 8 < p1) && !(o >= p1 && o + 8 < padded)) {
+      if (o < prefix_len) v |= piece(prefix, 0, prefix_len, o);
+      if (key && o + 8 > prefix_len && o < k1) {
+        v |= piece(hdr, prefix_len, k0, o);
+        v |= piece(key, k0, k1, o);
+      }
+      if (o + 8 > x0 && o < x1) v |= piece(x, x0, x1, o);
+      if (o + 8 > x1 && o < t1) v |= x1 >= o ? (uint64_t)trailer << (8 * (uint32_t)(x1 - o)) : (uint64_t)trailer >> (8 * (uint32_t)(o - x1));
+      if (has_pad1 && p1 - 1 >= o && p1 - 1 < o + 8) v |= 0x80ull << (8 * (uint32_t)(p1 - 1 - o));
+      if (has_pad && padded - 1 >= o && padded - 1 < o + 8) v |= 0x80ull << (8 * (uint32_t)(padded - 1 - o));
+    }
+    return v;
+  }
+
+  // blocks [fb0, fb1) lie wholly inside X (stride = bytes consumed per block)
+  __device__ __forceinline__ void fast_range(uint64_t stride, uint64_t skip_blocks, uint64_t& fb0, uint64_t& fb1) const {
+    fb0 = (x0 + stride - 1) / stride;
+    fb1 = x1 / stride;
+    if (fb0 < skip_blocks) fb0 = skip_blocks;
+    if (fb1 > nblocks) fb1 = nblocks;
+    if (fb1 < fb0) fb1 = fb0;
+    if (fb0 > nblocks) fb0 = fb1 = nblocks;
+  }
+};
+
+// =====================================================================================================
+// one thread per item
+// =====================================================================================================
 template <int LANES>
 __device__ __forceinline__ void sponge_item(const SpongeJob& J, uint64_t i) {
-  // ---- per-item stream geometry -----------------------------------------------------
-  const uint8_t* key = nullptr;
-  uint64_t klen = 0, kb_len = 0;
-  uint32_t w_nb = 1, k_nb = 1;
-  if (J.keys) {
-    if (J.key_off) {
-      key = J.keys + J.key_off[i];
-      klen = J.key_off[i + 1] - J.key_off[i];
-    } else {
-      key = J.keys + i * J.key_stride;
-      klen = J.key_len;
-    }
-    w_nb = left_encode_nbytes(J.w);
-    k_nb = left_encode_nbytes(klen * 8);
-    uint64_t content = (uint64_t)(1 + w_nb) + (1 + k_nb) + klen;
-    kb_len = (content / J.w + 1) * J.w;  // byte_pad always appends w - len % w zeros (quirk Q3)
-  }
-  const uint8_t* x;
-  uint64_t xlen;
-  if (J.off) {
-    x = J.data + J.off[i];
-    xlen = J.off[i + 1] - J.off[i];
-  } else {
-    x = J.data + i * J.msg_stride;
-    xlen = J.msg_len;
-  }
-  uint32_t trailer = J.trailer;
-  if (J.sha3_suffix) trailer = (xlen % 136u == 135u) ? 0x86u : 0x06u;
-  const uint64_t x0 = (uint64_t)J.prefix_len + kb_len;
-  const uint64_t x1 = x0 + xlen;
-  uint32_t trailer_len = J.trailer_len;
-  if (J.q4_rate) {  // shake_functions.rs:59-61 -> :25-29 on the buffer P|X|04
-    trailer |= (((x1 + 1) % 136u == 135u) ? 0x86u : 0x06u) << 8;
-    trailer_len = 2;
-  }
-  const uint64_t t1 = x1 + trailer_len;
-  // first pad (Q4 only): to a multiple of the SHA3-d rate, only when unaligned
-  uint64_t p1 = t1;
-  bool has_pad1 = false;
-  if (J.q4_rate) {
-    const uint64_t rem1 = t1 % J.q4_rate;
-    has_pad1 = rem1 != 0;
-    if (has_pad1) p1 = t1 + (J.q4_rate - rem1);
-  }
-  const uint64_t rem = p1 % J.rate;
-  const uint64_t padded = rem ? p1 + (J.rate - rem) : p1;  // Q1: no pad block when aligned
-  const uint64_t nblocks = padded / J.rate;
-  const bool has_pad = rem != 0;
-  if (J.fips_pad && !has_pad) trailer |= 0x80u << (8 * (trailer_len - 1));
-
+  SpongeGeom g;
+  g.init(J, i);
   Lane a[25];
   if (J.init_state) {
 #pragma unroll
     for (int k = 0; k < 25; k++) {
-      uint64_t v = J.init_state[k];
+      const uint64_t v = J.init_state[k];
       a[k].lo = (uint32_t)v;
       a[k].hi = (uint32_t)(v >> 32);
     }
@@ -158,59 +218,15 @@ __device__ __forceinline__ void sponge_item(const SpongeJob& J, uint64_t i) {
   // the long-message launch -- there is no other warp to hide the load latency).  The blocks before and
   // after that range touch a segment boundary and are assembled lane by lane from the virtual stream.
   constexpr uint64_t STRIDE = 8ull * LANES;  // bytes consumed per block (168 for the 172 quirk)
-  uint64_t fb0 = (x0 + STRIDE - 1) / STRIDE, fb1 = x1 / STRIDE;
-  if (fb0 < J.skip_blocks) fb0 = J.skip_blocks;
-  if (fb1 > nblocks) fb1 = nblocks;
-  if (fb1 < fb0) fb1 = fb0;
-  if (fb0 > nblocks) fb0 = fb1 = nblocks;
+  uint64_t fb0, fb1;
+  g.fast_range(STRIDE, J.skip_blocks, fb0, fb1);
+  const uint64_t nblocks = g.nblocks;
 
-  // Boundary blocks: a lane is the OR of the pieces of the (at most five) segments that overlap it, each piece
-  // fetched with a loop over just its own bytes; lanes wholly inside X, inside zero padding or past the end
-  // take one compare each.  (The first version walked all 8 bytes of every lane through a compare chain:
-  // ~2 700 instructions per block against ~700 now; KMAC over a 4 KB message has two such blocks in 33.)
-  uint8_t hdr[12];  // left_encode(w) || left_encode(8 * klen): the head of bytepad(encode_string(K), w)
-  uint32_t hdr_len = 0;
-  if (key) {
-    hdr[hdr_len++] = (uint8_t)w_nb;
-    for (uint32_t q = w_nb; q-- > 0;) hdr[hdr_len++] = (uint8_t)(J.w >> (8 * q));
-    hdr[hdr_len++] = (uint8_t)k_nb;
-    const uint64_t bits = klen * 8;
-    for (uint32_t q = k_nb; q-- > 0;) hdr[hdr_len++] = (uint8_t)(bits >> (8 * q));
-  }
-  const uint64_t k0 = (uint64_t)J.prefix_len + hdr_len;  // stream offset of the first key byte
-  const uint64_t k1 = k0 + klen;
-  // bytes of the segment [seg0, seg1) (stream offsets; base[0] sits at seg0) that fall into the lane at o
-  auto piece = [](const uint8_t* base, uint64_t seg0, uint64_t seg1, uint64_t o) -> uint64_t {
-    const uint64_t lo = o > seg0 ? o : seg0, hi = o + 8 < seg1 ? o + 8 : seg1;
-    uint64_t v = 0;
-#pragma unroll 1
-    for (uint64_t q = lo; q < hi; q++) v |= (uint64_t)base[q - seg0] << (8 * (uint32_t)(q - o));
-    return v;
-  };
   auto slow_block = [&](uint64_t b) {
     const uint64_t s = b * STRIDE;
     uint64_t blk[LANES];
 #pragma unroll 1
-    for (int j = 0; j < LANES; j++) {
-      const uint64_t o = s + 8ull * j;
-      uint64_t v = 0;
-      if (o >= x0 && o + 8 <= x1) {
-        const uint8_t* p = x + (o - x0);
-#pragma unroll
-        for (int k = 0; k < 8; k++) v |= (uint64_t)p[k] << (8 * k);
-      } else if (o < padded && !(o >= k1 && o + 8 <= x0) && !(o >= t1 && o + 8 < p1) && !(o >= p1 && o + 8 < padded)) {
-        if (o < J.prefix_len) v |= piece(J.prefix, 0, J.prefix_len, o);
-        if (key && o + 8 > J.prefix_len && o < k1) {
-          v |= piece(hdr, J.prefix_len, k0, o);
-          v |= piece(key, k0, k1, o);
-        }
-        if (o + 8 > x0 && o < x1) v |= piece(x, x0, x1, o);
-        if (o + 8 > x1 && o < t1) v |= x1 >= o ? (uint64_t)trailer << (8 * (uint32_t)(x1 - o)) : (uint64_t)trailer >> (8 * (uint32_t)(o - x1));
-        if (has_pad1 && p1 - 1 >= o && p1 - 1 < o + 8 && p1 - 1 >= t1) v |= 0x80ull << (8 * (uint32_t)(p1 - 1 - o));
-        if (has_pad && padded - 1 >= o && padded - 1 < o + 8 && padded - 1 >= t1) v |= 0x80ull << (8 * (uint32_t)(padded - 1 - o));
-      }
-      blk[j] = v;
-    }
+    for (int j = 0; j < LANES; j++) blk[j] = g.lane(s + 8ull * j);
 #pragma unroll
     for (int j = 0; j < LANES; j++) {
       a[j].lo ^= (uint32_t)blk[j];
@@ -225,7 +241,7 @@ __device__ __forceinline__ void sponge_item(const SpongeJob& J, uint64_t i) {
   // The choice between the 8-byte-aligned and the byte-phase load path is made PER WARP: a per-thread
   // branch here would put two separate permutation loops on the two sides of a divergent branch and
   // the warp would run both back to back (measured 2.1x slower on ragged batches).
-  const uint8_t* p = x + (fb0 * STRIDE - x0);
+  const uint8_t* p = g.x + (fb0 * STRIDE - g.x0);
   const bool has_fast = fb0 < fb1;
   const bool my_aligned = !has_fast || (reinterpret_cast<uintptr_t>(p) & 7u) == 0;
 #if defined(__CUDA_ARCH__)
@@ -329,11 +345,140 @@ __device__ __forceinline__ void sponge_item(const SpongeJob& J, uint64_t i) {
   }
 }
 
+// =====================================================================================================
+// two threads per item (keccak_pair.cuh): the even thread holds the low, the odd thread the high 32 bits of
+// every lane.  The permutation exchanges halves with full-warp shuffles, so the sixteen pairs of a warp walk ONE
+// warp-uniform step loop: step s of an item is "absorb block s", then "emit squeeze block s - absorbed", and every
+// step ends in a permutation that all 32 threads execute together; items that are already finished (the batch
+// is length-sorted, so the spread inside a warp is small) keep permuting a state nobody reads any more.
+// =====================================================================================================
+template <int LANES>
+__device__ __forceinline__ void sponge_item_pair(const SpongeJob& J, uint64_t i, bool valid, uint32_t half) {
+  constexpr uint64_t STRIDE = 8ull * LANES;
+  SpongeGeom g;
+  uint64_t fb0 = 0, fb1 = 0, n_absorb = 0, n_steps = 0;
+  uint8_t* o = nullptr;
+  const uint8_t* xi = nullptr;
+  uint64_t out_bytes = 0;
+  const uint64_t sq_bytes = 8ull * J.sq_lanes;
+  if (valid) {
+    g.init(J, i);
+    g.fast_range(STRIDE, J.skip_blocks, fb0, fb1);
+    n_absorb = g.nblocks - J.skip_blocks;
+    if (J.out_off) {
+      o = J.out + J.out_off[i];
+      out_bytes = J.out_off[i + 1] - J.out_off[i];
+    } else {
+      o = J.out + i * J.out_stride;
+      out_bytes = J.out_bytes;
+    }
+    xi = J.xor_in ? J.xor_in + (o - J.out) : nullptr;
+    // absorb steps, then one step per squeeze block except the last (no permutation follows it, quirk Q8)
+    n_steps = n_absorb + (out_bytes ? (out_bytes + sq_bytes - 1) / sq_bytes - 1 : 0);
+  }
+  const bool o_aligned = (reinterpret_cast<uintptr_t>(o) & 3u) == 0 && (!xi || (reinterpret_cast<uintptr_t>(xi) & 3u) == 0);
+  // warp-uniform trip count (64-bit maximum over the warp from two 32-bit reductions)
+  const uint32_t hi_max = __reduce_max_sync(0xffffffffu, (uint32_t)(n_steps >> 32));
+  const uint32_t lo_max = __reduce_max_sync(0xffffffffu, (uint32_t)(n_steps >> 32) == hi_max ? (uint32_t)n_steps : 0u);
+  const uint64_t warp_steps = ((uint64_t)hi_max << 32) | lo_max;
+
+  uint32_t h[25];
+#pragma unroll
+  for (int k = 0; k < 25; k++) h[k] = J.init_state ? (half ? (uint32_t)(J.init_state[k] >> 32) : (uint32_t)J.init_state[k]) : 0u;
+
+  // each thread streams only its own 32-bit half of every lane of the whole-message blocks; any byte phase:
+  // aligned words + funnel shift, next block prefetched before the permutation
+  const uint8_t* p = valid ? g.x + (fb0 * STRIDE - g.x0) : nullptr;
+  const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 3u) * 8u;
+  const uint32_t* q = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)3) + half;
+  uint32_t c0[LANES], c1[LANES];
+#pragma unroll
+  for (int j = 0; j < LANES; j++) c0[j] = c1[j] = 0u;
+  if (fb0 < fb1) {
+#pragma unroll
+    for (int j = 0; j < LANES; j++) {
+      c0[j] = __ldg(q + 2 * j);
+      c1[j] = sh != 0 ? __ldg(q + 2 * j + 1) : 0u;
+    }
+  }
+
+  auto emit = [&](uint64_t sb) {  // squeeze block sb of this item (sponge.rs:25-34)
+    const uint64_t produced = sb * sq_bytes;
+#pragma unroll
+    for (int j = 0; j < 21; j++) {
+      const uint64_t hp = produced + 8ull * j + 4ull * half;  // this thread's four bytes of lane j
+      if (j < (int)J.sq_lanes && hp < out_bytes) {
+        if (o_aligned && hp + 4 <= out_bytes) {
+          uint32_t v = h[j];
+          if (xi) v ^= *reinterpret_cast<const uint32_t*>(xi + hp);
+          *reinterpret_cast<uint32_t*>(o + hp) = v;
+        } else {
+          for (int k = 0; k < 4 && hp + k < out_bytes; k++) o[hp + k] = (uint8_t)(h[j] >> (8 * k)) ^ (xi ? xi[hp + k] : (uint8_t)0);
+        }
+      }
+    }
+  };
+
+#pragma unroll 1
+  for (uint64_t s = 0; s <= warp_steps; s++) {
+    if (s < n_absorb) {
+      const uint64_t b = J.skip_blocks + s;
+      if (b >= fb0 && b < fb1) {
+#pragma unroll
+        for (int j = 0; j < LANES; j++) h[j] ^= __funnelshift_r(c0[j], c1[j], sh);
+        q += 2 * LANES;
+        if (b + 1 < fb1) {
+#pragma unroll
+          for (int j = 0; j < LANES; j++) {
+            c0[j] = __ldg(q + 2 * j);
+            c1[j] = sh != 0 ? __ldg(q + 2 * j + 1) : 0u;
+          }
+        }
+      } else {
+        uint32_t blk[LANES];
+#pragma unroll 1
+        for (int j = 0; j < LANES; j++) {
+          const uint64_t v = g.lane(b * STRIDE + 8ull * j);
+          blk[j] = half ? (uint32_t)(v >> 32) : (uint32_t)v;
+        }
+#pragma unroll
+        for (int j = 0; j < LANES; j++) h[j] ^= blk[j];
+      }
+    } else if (s <= n_steps && out_bytes) {
+      emit(s - n_absorb);
+    }
+    if (s < warp_steps) keccak_f1600_pair(h, half);
+  }
+}
+
+// rank r of the (length-sorted) work list -> item index
+__device__ __forceinline__ uint64_t sponge_rank_item(const SpongeJob& J, uint64_t r) { return J.order ? (uint64_t)J.order[r] : r; }
+
+// one thread per item: ranks [J.first, J.n)
 template <int LANES>
 __global__ void __launch_bounds__(128, CAPY_SPONGE_MINB) sponge_kernel(const SpongeJob J) {
-  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= J.n) return;
-  sponge_item<LANES>(J, J.order ? (uint64_t)J.order[t] : t);
+  const uint64_t r = J.first + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= J.n) return;
+  sponge_item<LANES>(J, sponge_rank_item(J, r));
+}
+
+// Chain-bound ragged batch in ONE launch: blocks [0, pair_blocks) run two threads per item on ranks [0, J.first)
+// -- the longest messages -- and the remaining blocks one thread per item on ranks [J.first, J.n).  Blocks are
+// dispatched in index order, so the pair blocks are resident from the start (as a second kernel on another stream
+// they were starved behind the long-lived blocks of the thread-per-item kernel and ran after it).  Launched with
+// one 128-thread block per SM (shared-memory throttle): a chain advances fastest with its scheduler to itself.
+template <int LANES>
+__global__ void __launch_bounds__(128) sponge_tiered_kernel(const SpongeJob J, uint32_t pair_blocks) {
+  if (blockIdx.x < pair_blocks) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t r = t >> 1;
+    const bool valid = r < J.first;  // idle pairs of the last warp still take part in the shuffles
+    sponge_item_pair<LANES>(J, valid ? sponge_rank_item(J, r) : 0, valid, (uint32_t)(t & 1));
+  } else {
+    const uint64_t r = J.first + (uint64_t)(blockIdx.x - pair_blocks) * blockDim.x + threadIdx.x;
+    if (r >= J.n) return;
+    sponge_item<LANES>(J, sponge_rank_item(J, r));
+  }
 }
 
 }  // namespace capy

@@ -51,6 +51,9 @@ extern "C" {
 /* ragged batches are processed longest-message-first (device-side counting sort + one tiny D2H sync);
  * this flag keeps the caller's order and makes the _dev call fully asynchronous */
 #define CAPY_FLAG_NO_SORT 1u
+/* chain-bound ragged batches run their longest messages with two threads per message (the chain of one message
+ * advances faster); this flag keeps one thread per message everywhere (A/B measurements) */
+#define CAPY_FLAG_NO_PAIR 2u
 
 typedef struct capy_ctx capy_ctx;
 
