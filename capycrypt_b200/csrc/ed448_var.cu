@@ -87,7 +87,11 @@ __device__ __forceinline__ void pt_var_base_mul_hot(PtExt& r, const Sc& k, const
     PtCached e;
     vb_lookup(e, tab, (int)dig[i], constant_time);
     CAPY_VB_BARRIER();
+#ifdef CAPY_VB_ADD_OOL
+    pt_add_cached<true>(r, r, e);  // once per window: out-of-line multiplications keep the loop body small
+#else
     vb_add_hot(r, e);
+#endif
   }
 }
 #endif

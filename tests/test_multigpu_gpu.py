@@ -43,4 +43,17 @@ def test_multi_device_ctx_matches_single(engine, oracle):
     pub = eng2.ed448_keygen(pws, po, 512)
     rc, ok = eng2.ed448_verify(pub, md, mo, h2, z2, 512)
     assert rc == 0 and ok.all()
+    # authenticated encryption sharded the same way (ragged ciphertext ranges, per-device staging)
+    nonces = rnd.integers(0, 256, size=600 * 512, dtype=np.uint8)
+    c1, t1 = engine.sponge_encrypt(pws, po, nonces, 512, md, mo, 256)
+    c2, t2 = eng2.sponge_encrypt(pws, po, nonces, 512, md, mo, 256)
+    assert np.array_equal(c1, c2) and np.array_equal(t1, t2)
+    out, ok = eng2.sponge_decrypt(pws, po, nonces, 512, c2, mo, t2, 256)
+    assert ok.all() and np.array_equal(out, md)
+    k = rnd.integers(0, 256, size=600 * 56, dtype=np.uint8)
+    rc1, c1, t1, z1 = engine.ed448_key_encrypt(pub, k, md, mo, 512)
+    rc2, c2, t2, z2 = eng2.ed448_key_encrypt(pub, k, md, mo, 512)
+    assert rc1 == rc2 == 0 and np.array_equal(c1, c2) and np.array_equal(t1, t2) and np.array_equal(z1, z2)
+    rc, out, ok = eng2.ed448_key_decrypt(pws, po, z2, c2, mo, t2, 512)
+    assert rc == 0 and ok.all() and np.array_equal(out, md)
     eng2.close()
