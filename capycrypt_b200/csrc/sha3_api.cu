@@ -157,7 +157,8 @@ static inline unsigned grid_for(uint64_t n, unsigned block) { return (unsigned)(
 // processed longest first; when the longest chain would dominate, the launch is limited to 1-3 warps
 // per scheduler (dynamic shared memory as an occupancy throttle) so that chain advances at full speed.
 // ------------------------------------------------------------------------------------------------
-constexpr uint32_t kLenBins = 1u << 16;
+// 16 384 bins of one block each; longer messages (>= 1.1 MB at the SHA3-512 rate) share the last bin
+constexpr uint32_t kLenBins = 1u << 14;
 
 __device__ __forceinline__ uint32_t len_bin(const uint64_t* off, uint64_t i, uint32_t stride_bytes) {
   const uint64_t blocks = (off[i + 1] - off[i]) / stride_bytes;
@@ -170,42 +171,69 @@ __global__ void len_hist_kernel(const uint64_t* __restrict__ off, uint64_t n, ui
 }
 
 // hist[k] := number of items in bins > k (start of bin k in descending order); summary = {total blocks
-// (lo, hi), max bin, number of non-empty bins}
-__global__ void len_scan_kernel(uint32_t* hist, uint32_t* summary) {
+// (lo, hi), max bin, number of non-empty bins}.  1024 threads x 16 consecutive bins (four 128-bit loads each),
+// thread 0 owns the HIGHEST bins.
+__global__ void __launch_bounds__(1024) len_scan_kernel(uint32_t* hist, uint32_t* summary) {
   __shared__ uint32_t part[1024];
   __shared__ unsigned long long tot_s;
   __shared__ uint32_t max_s, bins_s;
-  const uint32_t t = threadIdx.x;  // 1024 threads x 64 bins, thread 0 owns the HIGHEST bins
-  constexpr uint32_t PER = kLenBins / 1024;
+  const uint32_t t = threadIdx.x;
+  constexpr uint32_t PER = kLenBins / 1024;  // 16
+  static_assert(PER == 16, "four uint4 per thread");
   if (t == 0) { tot_s = 0; max_s = 0; bins_s = 0; }
   __syncthreads();
-  const uint32_t hi = kLenBins - 1 - t * PER;  // bins hi, hi-1, ..., hi-PER+1
+  const uint32_t lo = kLenBins - (t + 1) * PER;  // this thread's bins lo .. lo + 15
+  uint32_t c[PER];
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    const uint4 v = reinterpret_cast<const uint4*>(hist + lo)[q];
+    c[4 * q] = v.x; c[4 * q + 1] = v.y; c[4 * q + 2] = v.z; c[4 * q + 3] = v.w;
+  }
   uint32_t sum = 0, nb = 0, mx = 0;
   unsigned long long tot = 0;
-  for (uint32_t k = 0; k < PER; k++) {
-    const uint32_t c = hist[hi - k];
-    sum += c;
-    if (c) { nb++; if (hi - k > mx) mx = hi - k; }
-    tot += (unsigned long long)c * (hi - k + 1);
+#pragma unroll
+  for (int k = 0; k < (int)PER; k++) {
+    sum += c[k];
+    if (c[k]) { nb++; mx = lo + k; }  // ascending k: the last non-empty one is the largest
+    tot += (unsigned long long)c[k] * (lo + k + 1);
   }
   part[t] = sum;
-  atomicAdd(&tot_s, tot);
-  atomicMax(&max_s, mx);
-  atomicAdd(&bins_s, nb);
+  if (sum) {
+    atomicAdd(&tot_s, tot);
+    atomicMax(&max_s, mx);
+    atomicAdd(&bins_s, nb);
+  }
   __syncthreads();
-  // exclusive scan of part[] (simple Hillis-Steele on 1024 entries)
-  for (uint32_t d = 1; d < 1024; d <<= 1) {
-    uint32_t v = t >= d ? part[t - d] : 0;
-    __syncthreads();
-    part[t] += v;
-    __syncthreads();
+  // inclusive scan of part[] over the threads (thread 0 = highest bins): warp shuffles, then the 32 warp totals
+  uint32_t incl = sum;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+    if ((t & 31) >= (uint32_t)d) incl += v;
   }
-  uint32_t run = part[t] - sum;  // items in bins above this thread's range
-  for (uint32_t k = 0; k < PER; k++) {
-    const uint32_t c = hist[hi - k];
-    hist[hi - k] = run;
-    run += c;
+  __shared__ uint32_t wsum[32];
+  if ((t & 31) == 31) wsum[t >> 5] = incl;
+  __syncthreads();
+  if (t < 32) {
+    uint32_t w = wsum[t];
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xffffffffu, w, d);
+      if (t >= (uint32_t)d) w += v;
+    }
+    wsum[t] = w;
   }
+  __syncthreads();
+  uint32_t run = incl - sum + ((t >> 5) ? wsum[(t >> 5) - 1] : 0u);  // items in bins above this thread's range
+  // descending inside the thread: bin lo + 15 first
+#pragma unroll
+  for (int k = (int)PER - 1; k >= 0; k--) {
+    const uint32_t cnt = c[k];
+    c[k] = run;
+    run += cnt;
+  }
+#pragma unroll
+  for (int q = 0; q < 4; q++) reinterpret_cast<uint4*>(hist + lo)[q] = make_uint4(c[4 * q], c[4 * q + 1], c[4 * q + 2], c[4 * q + 3]);
   if (t == 0) {
     summary[0] = (uint32_t)tot_s;
     summary[1] = (uint32_t)(tot_s >> 32);
