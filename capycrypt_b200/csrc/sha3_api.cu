@@ -391,15 +391,33 @@ static int launch_sha3(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t stream, int d,
   const uint32_t rate = (1600 - sha3_capacity(d)) / 8;  // 144 / 136 / 104 / 72
   const int lanes = (int)rate / 8;
   if (!off && (reinterpret_cast<uintptr_t>(data) & 15u) == 0 && (reinterpret_cast<uintptr_t>(out) & 15u) == 0 &&
-      (stride & 15u) == 0 && (d == 256 || d == 512) && (msg_len == 64 || msg_len == 32)) {
-    // compile-time block layout (cfg 1)
+      (stride & 15u) == 0 && (d == 256 || d == 512) && msg_len >= 16 && (msg_len & 15u) == 0 && msg_len < rate) {
+    // compile-time block layout: single-block messages of a whole number of 16-byte rows (cfg 1 is 64 B at D256)
     const unsigned block = 128, grid = grid_for(n, block);
     const uint4* dq = reinterpret_cast<const uint4*>(data);
     uint4* oq = reinterpret_cast<uint4*>(out);
-    if (d == 256 && msg_len == 64) sha3_short_kernel<17, 8><<<grid, block, 0, stream>>>(dq, stride / 16, 0x06u, oq, 32, n);
-    else if (d == 256) sha3_short_kernel<17, 4><<<grid, block, 0, stream>>>(dq, stride / 16, 0x06u, oq, 32, n);
-    else if (msg_len == 64) sha3_short_kernel<9, 8><<<grid, block, 0, stream>>>(dq, stride / 16, 0x06u, oq, 64, n);
-    else sha3_short_kernel<9, 4><<<grid, block, 0, stream>>>(dq, stride / 16, 0x06u, oq, 64, n);
+    const uint64_t s16 = stride / 16;
+#define CAPY_SHORT(L, M, OB) sha3_short_kernel<L, M><<<grid, block, 0, stream>>>(dq, s16, 0x06u, oq, OB, n)
+    if (d == 256) {
+      switch (msg_len / 8) {
+        case 2: CAPY_SHORT(17, 2, 32); break;
+        case 4: CAPY_SHORT(17, 4, 32); break;
+        case 6: CAPY_SHORT(17, 6, 32); break;
+        case 8: CAPY_SHORT(17, 8, 32); break;
+        case 10: CAPY_SHORT(17, 10, 32); break;
+        case 12: CAPY_SHORT(17, 12, 32); break;
+        case 14: CAPY_SHORT(17, 14, 32); break;
+        default: CAPY_SHORT(17, 16, 32); break;
+      }
+    } else {
+      switch (msg_len / 8) {
+        case 2: CAPY_SHORT(9, 2, 64); break;
+        case 4: CAPY_SHORT(9, 4, 64); break;
+        case 6: CAPY_SHORT(9, 6, 64); break;
+        default: CAPY_SHORT(9, 8, 64); break;
+      }
+    }
+#undef CAPY_SHORT
     ctx->launches++;
     CAPY_CUDA(ctx, cudaGetLastError());
     return CAPY_OK;

@@ -108,7 +108,9 @@ def test_sha3_ragged_long(engine, oracle, d):
 @pytest.mark.parametrize("d", DS)
 @pytest.mark.parametrize("msg_len,stride", [(64, 64), (32, 32), (32, 48), (64, 80), (0, 8), (1, 8), (63, 64), (71, 72), (135, 136), (136, 136),
                                              (143, 144), (200, 200), (1000, 1000), (4096, 4096), (100, 128),
-                                             (64, 65), (33, 33)])
+                                             (64, 65), (33, 33),
+                                             # every single-block length the compile-time specialised kernel takes
+                                             (16, 16), (48, 48), (80, 80), (96, 112), (112, 112), (128, 128), (128, 144)])
 def test_sha3_fixed(engine, oracle, d, msg_len, stride):
     """Uniform-length entry point (cfg-1 shape), aligned strides (fast kernel) and odd strides."""
     n = 777
