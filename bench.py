@@ -196,6 +196,27 @@ def live_peaks():
         return {**PEAK_FALLBACK, "source": f"profiles/r01_peaks_int_pipes.json (live run failed: {e!r})"}
 
 
+def bind_to_gpu_numa_node(local: int):
+    """Pins this rank's process to the CPUs NVML reports as closest to its GPU, so that the pinned host buffers of the
+    end-to-end leg are first-touched on that NUMA node (one process per GPU: without this all ranks' buffers tend to land
+    on one socket and the host side of PCIe becomes the bottleneck at N > 1).  Harness plumbing, not part of the engine."""
+    try:
+        import pynvml as nv
+
+        nv.nvmlInit()
+        h = nv.nvmlDeviceGetHandleByIndex(local)
+        ncpu = os.cpu_count() or 1
+        words = nv.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1 and 64 * w + b < ncpu}
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return {"cpus": len(allowed), "first": min(allowed), "last": max(allowed)}
+    except Exception as e:  # pragma: no cover
+        return {"error": repr(e)}
+    return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -216,6 +237,7 @@ def main():
     import torch
 
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(local)  # before any host buffer is allocated (first touch decides the NUMA node)
     dist = None
     if world > 1:
         import torch.distributed as dist_mod
@@ -290,7 +312,8 @@ def main():
     e2e = {"value": world * N_MSGS * MSG_LEN * k_e2e / e2e_s / 1e9, "unit": "GB/s",
            "h2d_bytes_per_step": N_MSGS * MSG_LEN, "d2h_bytes_per_step": N_MSGS * DIGEST, "steps": k_e2e,
            "ms_per_step": e2e_s / k_e2e * 1e3,
-           "api": "capy_sha3_batch_fixed (host buffers from capy_host_alloc, chunked H2D/kernel/D2H on 3 streams)"}
+           "api": "capy_sha3_batch_fixed (host buffers from capy_host_alloc, chunked H2D/kernel/D2H on 3 streams)",
+           "host_numa_binding": numa}
 
     # ---- roofline of the dominant kernel (sha3_short_kernel<17, 8>: one launch per step) ----
     ops = N_MSGS * OPS_PER_PERM
