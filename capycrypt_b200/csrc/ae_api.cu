@@ -354,6 +354,7 @@ using namespace capy;
 
 #define CAPY_DEV_PROLOGUE                                                                   \
   if (!ctx || dev_index < 0 || dev_index >= (int)ctx->devs.size()) return CAPY_ERR_BAD_ARG; \
+  std::lock_guard<std::mutex> lk(ctx->mu); /* host-side state (scratch slots, tables) is shared */ \
   DeviceCtx& dc = ctx->devs[dev_index];                                                     \
   DeviceGuard g(dc.dev);                                                                    \
   cudaStream_t st = (cudaStream_t)stream;

@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cstring>
 #include <thread>
+#include <vector>
 
 #include "internal.h"
 #include "hostbatch.h"
@@ -251,13 +252,60 @@ __global__ void len_scatter_kernel(const uint64_t* __restrict__ off, uint64_t n,
 struct LaunchPlan {
   const uint32_t* order = nullptr;
   int warps_per_smsp = 0;   // 0 = unthrottled
-  uint64_t pair_items = 0;  // ranks [0, pair_items) run two threads per item (sponge_pair_kernel)
+  uint64_t warp_items = 0;  // ranks [0, warp_items): one warp per item
+  uint64_t pair_items = 0;  // ranks [warp_items, warp_items + pair_items): two threads per item
 };
 
-// Measured on B200 at one warp per scheduler: a thread-per-state chain advances one permutation per 4.55 us, a
-// thread pair one per 3.35 us in isolation (csrc/keccak_pair_probe.cu) and per 3.7-3.95 us inside the sponge
-// (absorb loads, warp-uniform step loop; 1 024 x 1 MiB SHA3-512: 53.6 ms against 67.0 ms).
+// Measured on B200 at one warp per scheduler, per permutation of ONE chain: one thread per state 4.55 us; a thread
+// pair 3.35 us in isolation (csrc/keccak_pair_probe.cu) and 3.7-3.95 us inside the sponge (absorb loads, warp-uniform
+// step loop; 1 024 x 1 MiB SHA3-512: 53.6 ms against 67.0 ms); a whole warp per state 2.18 us in isolation and
+// 2.95 us inside the sponge (64 x 1 MiB: 43 ms against 67 ms).
 constexpr double kPairChainRatio = 3.95 / 4.6;
+constexpr double kWarpChainRatio = 3.0 / 4.6;
+
+// Tiers of a chain-bound batch.  cum[k] = number of items in length bins > k (bin = whole blocks of the message).
+// Times are in units of one thread-per-state permutation; an SM hosts ONE block: 4 warp-tier, 64 pair-tier or 128
+// thread-tier items.  The smallest step time T is searched for which (a) every chain fits its tier, (b) the blocks of
+// the two fast tiers are all resident from the start and (c) the thread tier fits on the SMs that are left.
+static void plan_tiers(const std::vector<uint32_t>& cum, uint64_t n, uint32_t max_blocks, double total_blocks, int sm_count,
+                       uint64_t* warp_items, uint64_t* pair_items) {
+  *warp_items = *pair_items = 0;
+  const size_t nb = cum.size();
+  std::vector<double> work_above(nb);  // blocks in bins > k
+  double acc = 0;
+  for (size_t k = nb; k-- > 0;) {
+    work_above[k] = acc;
+    const uint64_t cnt = (k == 0 ? n : cum[k - 1]) - cum[k];
+    acc += (double)cnt * (double)(k + 1);
+  }
+  auto longer_than = [&](double thr, uint64_t* count, double* work) {  // items whose chain (bin + 1) exceeds thr
+    if (thr < 1.0) {
+      *count = n;
+      *work = total_blocks;
+      return;
+    }
+    const size_t k = std::min<size_t>((size_t)thr - 1, nb - 1);
+    *count = cum[k];
+    *work = work_above[k];
+  };
+  const double l1 = (double)max_blocks;
+  for (double T = l1 * kWarpChainRatio; T < l1; T *= 1.04) {
+    uint64_t k_fast, k_w;
+    double w_fast, w_w;
+    longer_than(T, &k_fast, &w_fast);                 // must not run one thread per item
+    longer_than(T / kPairChainRatio, &k_w, &w_w);     // must not even run as a pair
+    if (k_w == 0 && T < l1 * kPairChainRatio) continue;  // (the pair tier alone cannot finish the longest item in T)
+    const uint64_t k_p = k_fast - k_w;
+    const uint64_t blocks = (k_w + 3) / 4 + (k_p + 63) / 64;
+    if (blocks + 1 > (uint64_t)sm_count) continue;
+    // the thread-per-item tier gets the SMs the fast tiers leave (those stay busy for about T: their items are the
+    // longest); its items are dispatched longest first, so it needs its share of SMs from the start
+    if ((total_blocks - w_fast) / 128.0 > T * (double)((uint64_t)sm_count - blocks)) continue;
+    *warp_items = k_w;
+    *pair_items = k_p;
+    return;
+  }
+}
 
 // builds the descending-length order for a ragged batch; decides the occupancy throttle and how many of the
 // longest items go to the two-threads-per-item kernel
@@ -284,20 +332,12 @@ static int plan_ragged(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t st, const uint
   // time in units of one thread-per-state permutation on one scheduler: all work spread over every scheduler
   // (32 states per warp, one warp per scheduler) vs the longest chain
   const double ideal = (double)total_blocks / (32.0 * 4.0 * dc.sm_count);
-  // Chain-bound batch: every item whose own chain would outlast the work-bound time goes to the pair kernel,
-  // which occupies whole SMs (64 items each) next to the thread-per-item kernel.  At most half of the SMs.
-  const uint64_t pair_cap = 64ull * (uint64_t)(dc.sm_count / 2);
+  // Chain-bound batch: the longest items go to the warp-per-item and the two-threads-per-item tiers
   if (allow_pair && max_blocks > 64 && (double)max_blocks > 1.05 * ideal) {
-    const double target = std::max(1.03 * ideal, kPairChainRatio * (double)max_blocks);
-    uint64_t need = n;
-    if (bins > 1 && target < (double)max_blocks) {
-      const uint32_t tb = std::min<uint32_t>((uint32_t)target, kLenBins - 1);
-      uint32_t above = 0;  // after the scan hist[k] = number of items in bins > k
-      CAPY_CUDA(ctx, cudaMemcpyAsync(&above, hist + tb, sizeof above, cudaMemcpyDeviceToHost, st));
-      CAPY_CUDA(ctx, cudaStreamSynchronize(st));
-      need = above;
-    }
-    plan->pair_items = std::min<uint64_t>(std::min<uint64_t>((need + 63) / 64 * 64, pair_cap), n);
+    std::vector<uint32_t> cum(kLenBins);  // after the scan hist[k] = number of items in bins > k
+    CAPY_CUDA(ctx, cudaMemcpyAsync(cum.data(), hist, (size_t)kLenBins * 4, cudaMemcpyDeviceToHost, st));
+    CAPY_CUDA(ctx, cudaStreamSynchronize(st));
+    plan_tiers(cum, n, max_blocks, (double)total_blocks, dc.sm_count, &plan->warp_items, &plan->pair_items);
   }
   if (bins <= 1) return CAPY_OK;  // uniform lengths: nothing to order
   len_scatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_off, n, stride_bytes, hist, order);
@@ -315,14 +355,16 @@ static int plan_ragged(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t st, const uint
 
 template <int LANES>
 static int launch_sponge_t(capy_ctx* ctx, cudaStream_t stream, SpongeJob J, unsigned block, int warps_per_smsp,
-                           uint64_t pair_items) {
-  if (pair_items) {
-    // chain-bound batch: pair blocks first, then thread-per-item blocks, one block per SM
+                           uint64_t warp_items, uint64_t pair_items) {
+  if (pair_items || warp_items) {
+    // chain-bound batch: warp blocks, then pair blocks, then thread-per-item blocks, one block per SM
+    const unsigned warp_blocks = grid_for(warp_items, 4);
     const unsigned pair_blocks = grid_for(2 * pair_items, 128);
-    const unsigned solo_blocks = grid_for(J.n - pair_items, 128);
-    J.first = pair_items;
+    const unsigned solo_blocks = grid_for(J.n - pair_items - warp_items, 128);
+    J.warp_items = warp_items;
+    J.first = warp_items + pair_items;
     CAPY_CUDA(ctx, cudaFuncSetAttribute(sponge_tiered_kernel<LANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-    sponge_tiered_kernel<LANES><<<pair_blocks + solo_blocks, 128, 226 * 1024, stream>>>(J, pair_blocks);
+    sponge_tiered_kernel<LANES><<<warp_blocks + pair_blocks + solo_blocks, 128, 226 * 1024, stream>>>(J, warp_blocks, pair_blocks);
     ctx->launches++;
     CAPY_CUDA(ctx, cudaGetLastError());
     return CAPY_OK;
@@ -367,12 +409,12 @@ static int launch_sponge(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t stream, int 
   const int w = plan.warps_per_smsp;
   const uint64_t pi = plan.pair_items;
   switch (lanes) {
-    case 9: return launch_sponge_t<9>(ctx, stream, J, block, w, pi);
-    case 13: return launch_sponge_t<13>(ctx, stream, J, block, w, pi);
-    case 17: return launch_sponge_t<17>(ctx, stream, J, block, w, pi);
-    case 18: return launch_sponge_t<18>(ctx, stream, J, block, w, pi);
-    case 19: return launch_sponge_t<19>(ctx, stream, J, block, w, pi);
-    case 21: return launch_sponge_t<21>(ctx, stream, J, block, w, pi);
+    case 9: return launch_sponge_t<9>(ctx, stream, J, block, w, plan.warp_items, pi);
+    case 13: return launch_sponge_t<13>(ctx, stream, J, block, w, plan.warp_items, pi);
+    case 17: return launch_sponge_t<17>(ctx, stream, J, block, w, plan.warp_items, pi);
+    case 18: return launch_sponge_t<18>(ctx, stream, J, block, w, plan.warp_items, pi);
+    case 19: return launch_sponge_t<19>(ctx, stream, J, block, w, plan.warp_items, pi);
+    case 21: return launch_sponge_t<21>(ctx, stream, J, block, w, plan.warp_items, pi);
     default: return CAPY_ERR_BAD_ARG;
   }
 }
@@ -608,6 +650,7 @@ int capy_sha3_batch_dev(capy_ctx* ctx, int dev_index, void* stream, int d_bits, 
                         const uint64_t* d_off, uint64_t n, uint8_t* d_digests, uint32_t flags) {
   if (!ctx || dev_index < 0 || dev_index >= (int)ctx->devs.size() || (n && (!d_data || !d_off || !d_digests)))
     return CAPY_ERR_BAD_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);  // host-side state (scratch slots, prefix cache) is shared
   DeviceGuard g(ctx->devs[dev_index].dev);
   return launch_sha3(ctx, ctx->devs[dev_index], (cudaStream_t)stream, d_bits, d_data, d_off, 0, 0, n, d_digests, flags);
 }
@@ -616,6 +659,7 @@ int capy_sha3_batch_fixed_dev(capy_ctx* ctx, int dev_index, void* stream, int d_
                               uint64_t msg_len, uint64_t stride, uint64_t n, uint8_t* d_digests, uint32_t) {
   if (!ctx || dev_index < 0 || dev_index >= (int)ctx->devs.size() || (n && (!d_data || !d_digests)) || stride < msg_len)
     return CAPY_ERR_BAD_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);  // host-side state (scratch slots, prefix cache) is shared
   DeviceGuard g(ctx->devs[dev_index].dev);
   return launch_sha3(ctx, ctx->devs[dev_index], (cudaStream_t)stream, d_bits, d_data, nullptr, msg_len, stride, n, d_digests);
 }
@@ -692,6 +736,7 @@ int capy_cshake_batch_dev(capy_ctx* ctx, int dev_index, void* stream, int d_bits
   if (!ctx || dev_index < 0 || dev_index >= (int)ctx->devs.size() || (n && (!d_data || !d_off || !d_out)) ||
       (fn_len && !fn_name) || (custom_len && !custom))
     return CAPY_ERR_BAD_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);  // host-side state (scratch slots, prefix cache) is shared
   DeviceCtx& dc = ctx->devs[dev_index];
   DeviceGuard g(dc.dev);
   return launch_cshake(ctx, dc, (cudaStream_t)stream, d_bits, d_data, d_off, n, fn_name, fn_len, custom, custom_len,
@@ -739,6 +784,7 @@ int capy_kmac_xof_batch_dev(capy_ctx* ctx, int dev_index, void* stream, int d_bi
   if (!ctx || dev_index < 0 || dev_index >= (int)ctx->devs.size() ||
       (n && (!d_keys || !d_key_off || !d_data || !d_off || !d_out)) || (custom_len && !custom))
     return CAPY_ERR_BAD_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);  // host-side state (scratch slots, prefix cache) is shared
   DeviceCtx& dc = ctx->devs[dev_index];
   DeviceGuard g(dc.dev);
   KmacDevArgs a{};
@@ -763,6 +809,7 @@ int capy_kmac_xof_batch_fixed_dev(capy_ctx* ctx, int dev_index, void* stream, in
   if (!ctx || dev_index < 0 || dev_index >= (int)ctx->devs.size() || (n && (!d_keys || !d_out)) ||
       (n && msg_len && !d_data) || (custom_len && !custom) || key_stride < key_len || msg_stride < msg_len)
     return CAPY_ERR_BAD_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);  // host-side state (scratch slots, prefix cache) is shared
   DeviceCtx& dc = ctx->devs[dev_index];
   DeviceGuard g(dc.dev);
   KmacDevArgs a{};
@@ -847,6 +894,7 @@ int capy_fips_shake_batch_dev(capy_ctx* ctx, int dev_index, void* stream, int sh
       (shake_bits != 128 && shake_bits != 256))
     return CAPY_ERR_BAD_ARG;
   if (n == 0 || out_bytes == 0) return CAPY_OK;
+  std::lock_guard<std::mutex> lk(ctx->mu);  // host-side state (scratch slots, prefix cache) is shared
   DeviceGuard g(ctx->devs[dev_index].dev);
   SpongeJob J = empty_job();
   J.data = d_data;

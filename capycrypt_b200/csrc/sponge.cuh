@@ -65,7 +65,9 @@ struct SpongeJob {
   uint64_t n;
   // optional permutation of work: item index = order ? order[r] : r for rank r (length-sorted launch)
   const uint32_t* order;
-  // ranks [0, first) belong to sponge_pair_kernel (two threads per item), [first, n) to sponge_kernel
+  // tiers of a chain-bound batch (sponge_tiered_kernel): ranks [0, warp_items) one warp per item,
+  // [warp_items, first) two threads per item, [first, n) one thread per item
+  uint64_t warp_items;
   uint64_t first;
 };
 
@@ -451,6 +453,95 @@ __device__ __forceinline__ void sponge_item_pair(const SpongeJob& J, uint64_t i,
   }
 }
 
+// =====================================================================================================
+// one WARP per item (WarpKeccak): thread l owns lane l, absorbs its own 8 bytes of every block (a warp reads one
+// message as contiguous 72..168-byte rows) and emits its own lane of every squeeze block
+// =====================================================================================================
+template <int LANES>
+__device__ __noinline__ void sponge_item_warp(const SpongeJob& J, uint64_t i) {  // own register allocation: fused inline it slowed the other tiers
+  constexpr uint64_t STRIDE = 8ull * LANES;
+  const int l = threadIdx.x & 31;
+  const bool mine = l < LANES;
+  SpongeGeom g;
+  g.init(J, i);
+  uint64_t fb0, fb1;
+  g.fast_range(STRIDE, J.skip_blocks, fb0, fb1);
+  WarpKeccak wk;
+  wk.init(l);
+  uint32_t lo = 0, hi = 0;
+  if (J.init_state && l < 25) {
+    const uint64_t v = J.init_state[l];
+    lo = (uint32_t)v;
+    hi = (uint32_t)(v >> 32);
+  }
+  // whole-message blocks: this thread's lane as three aligned words + funnel shift, next block prefetched
+  const uint8_t* p = g.x + (fb0 * STRIDE - g.x0) + 8ull * (mine ? l : 0);
+  const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 3u) * 8u;
+  const uint32_t* q = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)3);
+  uint32_t w0 = 0, w1 = 0, w2 = 0;
+  if (fb0 < fb1 && mine) {
+    w0 = __ldg(q);
+    w1 = __ldg(q + 1);
+    w2 = sh != 0 ? __ldg(q + 2) : 0u;
+  }
+#pragma unroll 1
+  for (uint64_t b = J.skip_blocks; b < g.nblocks; b++) {
+    uint32_t vlo = 0, vhi = 0;
+    if (b >= fb0 && b < fb1) {
+      vlo = __funnelshift_r(w0, w1, sh);
+      vhi = __funnelshift_r(w1, w2, sh);
+      q += 2 * LANES;
+      if (b + 1 < fb1 && mine) {
+        w0 = __ldg(q);
+        w1 = __ldg(q + 1);
+        w2 = sh != 0 ? __ldg(q + 2) : 0u;
+      }
+    } else if (mine) {
+      const uint64_t v = g.lane(b * STRIDE + 8ull * l);
+      vlo = (uint32_t)v;
+      vhi = (uint32_t)(v >> 32);
+    }
+    if (mine) {
+      lo ^= vlo;
+      hi ^= vhi;
+    }
+    wk.permute(lo, hi);
+  }
+  // squeeze (sponge.rs:25-34, minus the dropped final permutation)
+  uint8_t* o;
+  uint64_t out_bytes;
+  if (J.out_off) {
+    o = J.out + J.out_off[i];
+    out_bytes = J.out_off[i + 1] - J.out_off[i];
+  } else {
+    o = J.out + i * J.out_stride;
+    out_bytes = J.out_bytes;
+  }
+  const uint64_t sq_bytes = 8ull * J.sq_lanes;
+  const uint8_t* xi = J.xor_in ? J.xor_in + (o - J.out) : nullptr;
+  const bool o_aligned = (reinterpret_cast<uintptr_t>(o) & 7u) == 0 && (!xi || (reinterpret_cast<uintptr_t>(xi) & 7u) == 0);
+#pragma unroll 1
+  for (uint64_t produced = 0; produced < out_bytes;) {
+    const uint64_t pos = produced + 8ull * l;
+    if (l < (int)J.sq_lanes && pos < out_bytes) {
+      if (o_aligned && pos + 8 <= out_bytes) {
+        uint2 v = make_uint2(lo, hi);
+        if (xi) {
+          const uint2 mm = *reinterpret_cast<const uint2*>(xi + pos);
+          v.x ^= mm.x;
+          v.y ^= mm.y;
+        }
+        *reinterpret_cast<uint2*>(o + pos) = v;
+      } else {
+        const uint64_t v = ((uint64_t)hi << 32) | lo;
+        for (int k = 0; k < 8 && pos + k < out_bytes; k++) o[pos + k] = (uint8_t)(v >> (8 * k)) ^ (xi ? xi[pos + k] : (uint8_t)0);
+      }
+    }
+    produced += sq_bytes;
+    if (produced < out_bytes) wk.permute(lo, hi);
+  }
+}
+
 // rank r of the (length-sorted) work list -> item index
 __device__ __forceinline__ uint64_t sponge_rank_item(const SpongeJob& J, uint64_t r) { return J.order ? (uint64_t)J.order[r] : r; }
 
@@ -462,22 +553,39 @@ __global__ void __launch_bounds__(128, CAPY_SPONGE_MINB) sponge_kernel(const Spo
   sponge_item<LANES>(J, sponge_rank_item(J, r));
 }
 
-// Chain-bound ragged batch in ONE launch: blocks [0, pair_blocks) run two threads per item on ranks [0, J.first)
-// -- the longest messages -- and the remaining blocks one thread per item on ranks [J.first, J.n).  Blocks are
-// dispatched in index order, so the pair blocks are resident from the start (as a second kernel on another stream
-// they were starved behind the long-lived blocks of the thread-per-item kernel and ran after it).  Launched with
-// one 128-thread block per SM (shared-memory throttle): a chain advances fastest with its scheduler to itself.
+// Chain-bound ragged batch in ONE launch, three tiers by rank in the length-sorted order:
+//   blocks [0, warp_blocks)                        one WARP per item   ranks [0, J.warp_items)        4 items per block
+//   blocks [warp_blocks, warp_blocks + pair_blocks) two threads per item ranks [J.warp_items, J.first)  64 items per block
+//   the remaining blocks                            one thread per item  ranks [J.first, J.n)          128 items per block
+// Blocks are dispatched in index order, so the blocks with the longest chains are resident from the start (as a
+// second kernel on another stream they were starved behind the long-lived blocks of the thread-per-item kernel and
+// ran after it).  Launched with one 128-thread block per SM (shared-memory throttle): a chain advances fastest with
+// its scheduler to itself.
+// The three tiers are compiled as separate (out-of-line) functions: inlined into one kernel body they share one
+// register allocation and instruction schedule, which slowed the thread-per-item chain from 4.6 to 5.4 us per
+// permutation.
 template <int LANES>
-__global__ void __launch_bounds__(128) sponge_tiered_kernel(const SpongeJob J, uint32_t pair_blocks) {
-  if (blockIdx.x < pair_blocks) {
-    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const uint64_t r = t >> 1;
+__device__ __noinline__ void sponge_item_solo_ool(const SpongeJob& J, uint64_t i) { sponge_item<LANES>(J, i); }
+template <int LANES>
+__device__ __noinline__ void sponge_item_pair_ool(const SpongeJob& J, uint64_t i, bool valid, uint32_t half) {
+  sponge_item_pair<LANES>(J, i, valid, half);
+}
+
+template <int LANES>
+__global__ void __launch_bounds__(128) sponge_tiered_kernel(const SpongeJob J, uint32_t warp_blocks, uint32_t pair_blocks) {
+  if (blockIdx.x < warp_blocks) {
+    const uint64_t r = (uint64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (r >= J.warp_items) return;  // whole warps leave together
+    sponge_item_warp<LANES>(J, sponge_rank_item(J, r));
+  } else if (blockIdx.x < warp_blocks + pair_blocks) {
+    const uint64_t t = (uint64_t)(blockIdx.x - warp_blocks) * blockDim.x + threadIdx.x;
+    const uint64_t r = J.warp_items + (t >> 1);
     const bool valid = r < J.first;  // idle pairs of the last warp still take part in the shuffles
-    sponge_item_pair<LANES>(J, valid ? sponge_rank_item(J, r) : 0, valid, (uint32_t)(t & 1));
+    sponge_item_pair_ool<LANES>(J, valid ? sponge_rank_item(J, r) : 0, valid, (uint32_t)(t & 1));
   } else {
-    const uint64_t r = J.first + (uint64_t)(blockIdx.x - pair_blocks) * blockDim.x + threadIdx.x;
+    const uint64_t r = J.first + (uint64_t)(blockIdx.x - warp_blocks - pair_blocks) * blockDim.x + threadIdx.x;
     if (r >= J.n) return;
-    sponge_item<LANES>(J, sponge_rank_item(J, r));
+    sponge_item_solo_ool<LANES>(J, sponge_rank_item(J, r));
   }
 }
 

@@ -24,6 +24,9 @@
  *  - field elements: 56 bytes little-endian canonical (FieldElement::to_bytes);
  *    scalars: 56 bytes big-endian (aux_functions.rs:102-110); points: affine x || y, 112 bytes.
  *  - deterministic: no RNG inside; nonces are inputs.
+ *  - `_dev` calls only enqueue work (ragged batches also read one small summary back to plan their launch).
+ *    They share the ctx's device scratch buffers, so the `_dev` calls of one ctx must be issued on ONE stream at a
+ *    time; use one ctx per concurrently used stream.
  *  - a ctx may span several GPUs; host entry points shard the batch across them by contiguous
  *    ranges (no collective: items are independent).  Calls on one ctx are serialised by an
  *    internal mutex; distinct ctxs are independent.

@@ -1,7 +1,8 @@
-"""GPU: the two-threads-per-item tier of ragged sponge batches (csrc/keccak_pair.cuh, sponge_pair_kernel).
+"""GPU: the fast tiers of chain-bound ragged sponge batches (csrc/keccak_pair.cuh, sponge_tiered_kernel).
 
-A sponge is sequential per message, so a batch whose longest chain outlasts the work-bound time sends its longest items
-to a kernel in which two adjacent threads share one state (low / high 32 bits of every lane).  Every digest, tag and
+A sponge is sequential per message, so a batch whose longest chain outlasts the work-bound time runs its longest
+items with a whole warp per message (one lane per thread) or with two adjacent threads per message (low / high 32
+bits of every lane); the small batches below land in the warp tier, the larger ones spread over all three tiers.  Every digest, tag and
 keystream byte must be identical to the thread-per-item path and to the oracle (sha3/sponge.rs:10-34,
 sha3/shake_functions.rs:24-89), including the reference's padding quirks at the block boundaries."""
 import random
