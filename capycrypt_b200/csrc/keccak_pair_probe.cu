@@ -66,6 +66,26 @@ __global__ void __launch_bounds__(128) chain_warp25(uint64_t* st, int nperm) {
   if (l < 25) st[(size_t)item * 25 + l] = ((uint64_t)hi << 32) | lo;
 }
 
+// the same permutation through the WarpKeccak struct the sponge uses, with an early exit in front (what the
+// tiered kernel has) and one XOR per permutation standing in for the absorb
+__global__ void __launch_bounds__(128) chain_warp25_struct(uint64_t* st, int nperm, int n_items, const uint32_t* __restrict__ feed) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int item = t >> 5;
+  if (item >= n_items) return;
+  const int l = threadIdx.x & 31;
+  WarpKeccak wk;
+  wk.init(l);
+  const uint64_t v = st[(size_t)item * 25 + (l < 25 ? l : 0)];
+  uint32_t lo = (uint32_t)v, hi = (uint32_t)(v >> 32);
+  uint32_t w = feed ? __ldg(feed + t) : 0u;
+  for (int p = 0; p < nperm; p++) {
+    if (l < 9) lo ^= w;
+    if (feed && p + 1 < nperm) w = __ldg(feed + t + (size_t)(p + 1) * 32);
+    wk.permute(lo, hi);
+  }
+  if (l < 25) st[(size_t)item * 25 + l] = ((uint64_t)hi << 32) | lo;
+}
+
 int main(int argc, char** argv) {
   const int nperm = argc > 1 ? atoi(argv[1]) : 2000;
   cudaDeviceProp prop; cudaGetDeviceProperties(&prop, 0);
@@ -101,6 +121,16 @@ int main(int argc, char** argv) {
       printf("{\"warps_per_scheduler\": %d, \"warp25_us_per_perm\": %.4f, \"chain_speedup_vs_single\": %.3f, \"warp25_Gperm_s\": %.4f, \"mismatching_lanes\": %zu}\n",
              wps, ms3 * 1e3 / nperm, ms1 / ms3, threads / 32 / (ms3 * 1e-3 / nperm) / 1e9, bad3);
       cudaFree(d3);
+    }
+    {
+      uint64_t* d4; cudaMalloc(&d4, init.size() * 8);
+      cudaMemcpy(d4, init.data(), init.size() * 8, cudaMemcpyHostToDevice);
+      chain_warp25_struct<<<blocks, 128>>>(d4, 2, threads / 32, nullptr);
+      float ms4;
+      cudaEventRecord(e0); chain_warp25_struct<<<blocks, 128>>>(d4, nperm, threads / 32, nullptr); cudaEventRecord(e1); cudaEventSynchronize(e1);
+      cudaEventElapsedTime(&ms4, e0, e1);
+      printf("{\"warps_per_scheduler\": %d, \"warp25_struct_early_exit_us_per_perm\": %.4f}\n", wps, ms4 * 1e3 / nperm);
+      cudaFree(d4);
     }
     // pair kernel covers threads/2 items: compare those
     std::vector<uint64_t> r1((size_t)threads * 25), r2((size_t)threads * 25);
