@@ -139,6 +139,52 @@ def cpu_sha3_baseline(budget_s: float, threads: int = 0):
     }
 
 
+def cpu_ed448_baseline(budget_s: float, threads: int = 0):
+    """The Ed448 half of the metric on the host: KeyPair::new-style [s]G (the reference multiplies the generator with
+    its generic variable-base routine, ecc/keypair.rs:44), sign and verify, through the C restatement on `threads`
+    host threads (0 = all).  Bounded samples sized from a calibration run."""
+    import numpy as np
+
+    from oracle import cpu
+
+    orc = cpu.get(native=True)
+    cores = orc.max_threads if threads <= 0 else threads
+    rng = np.random.default_rng(3)
+
+    def rate(fn, n_cal, make):
+        args = make(n_cal)
+        fn(*args)
+        t0 = time.perf_counter()
+        fn(*args)
+        r = n_cal / (time.perf_counter() - t0)
+        n = int(max(n_cal, min(1 << 16, r * budget_s)))
+        args = make(n)
+        t0 = time.perf_counter()
+        fn(*args)
+        return n / (time.perf_counter() - t0), n
+
+    def mk_sc(n):
+        return (rng.integers(0, 256, size=n * 56, dtype=np.uint8),)
+
+    def mk_sign(n):
+        pw = rng.integers(0, 256, size=n * 32, dtype=np.uint8)
+        msg = rng.integers(0, 256, size=n * 256, dtype=np.uint8)
+        return pw, np.arange(n + 1, dtype=np.uint64) * 32, msg, np.arange(n + 1, dtype=np.uint64) * 256
+
+    fb, n_fb = rate(lambda sc: orc.fixed_base_batch(sc, threads=threads), 256, mk_sc)
+    sg, n_sg = rate(lambda pw, po, m, mo: orc.sign_batch(pw, po, m, mo, 512, threads=threads), 256, mk_sign)
+    pw, po, m, mo = mk_sign(min(n_sg, 2048))
+    pub = orc.keygen_batch(pw, po, 512, threads=threads)
+    h, z = orc.sign_batch(pw, po, m, mo, 512, threads=threads)
+    t0 = time.perf_counter()
+    orc.verify_batch(pub, m, mo, h, z, 512, threads=threads)
+    vf = (len(po) - 1) / (time.perf_counter() - t0)
+    return {"scalar_mults_per_s": fb, "signs_per_s": sg, "verifies_per_s": vf, "unit": "1/s", "cores": cores, "kind": "port",
+            "sample": f"{n_fb} generator multiplications, {n_sg} signatures, {len(po) - 1} verifications (32-byte passwords, "
+                      f"256-byte messages, D512), oracle/ref_cpu.c (64-bit limbs, u128 products, signed radix-16 window like "
+                      f"the crate), gcc -O3 -march=native, {cores} threads"}
+
+
 def run_reference(args, rank: int):
     """--impl reference: the reference's own CPU implementation of the path on the host cores.  The Rust
     reference cannot be built in this image (no rustc/cargo), so this is the oracle port."""
@@ -179,6 +225,7 @@ def run_reference(args, rank: int):
         "cpu_baseline": {"value": gbps, "unit": "GB/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": gbps, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "extra": {"ed448_cpu": cpu_ed448_baseline(budget_s=1.0)},
     }
     print(json.dumps(line), flush=True)
 
@@ -356,6 +403,7 @@ def main():
         line["extra"] = extras(eng, dev, peaks, world, dist, rank)
     if rank == 0 and world == 1 and not args.no_cpu:
         line["cpu_baseline"] = cpu_sha3_baseline(budget_s=1.5)
+        line["cpu_baseline"]["ed448"] = cpu_ed448_baseline(budget_s=1.0)
     elif rank == 0:
         line["cpu_baseline"] = None
     eng.close()
