@@ -227,7 +227,7 @@ def run_reference(args, rank: int):
         "gpu_launches": 0,
         "extra": {"ed448_cpu": cpu_ed448_baseline(budget_s=1.0)},
     }
-    print(json.dumps(line), flush=True)
+    emit_json_line(line)
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -264,7 +264,31 @@ def bind_to_gpu_numa_node(local: int):
     return None
 
 
+_REAL_STDOUT = None
+
+
+def keep_stdout_for_the_json_line():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner to stdout when
+    NCCL_DEBUG is set), so file descriptor 1 is pointed at stderr for the whole run and the line goes to a saved copy
+    of the original stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit_json_line(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    keep_stdout_for_the_json_line()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=2000)
@@ -411,7 +435,7 @@ def main():
         dist.barrier()
         dist.destroy_process_group()
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit_json_line(line)
 
 
 def extras(eng, dev, peaks, world, dist, rank):
