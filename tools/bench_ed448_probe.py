@@ -1,5 +1,7 @@
 # development aid (not the contract bench): device-resident Ed448 throughput of one library variant.
 # usage: CAPY_GPU_LIB=<path> python bench_ed448_probe.py
+import os as _os, sys as _sys
+_sys.path.insert(0, _os.path.join(_os.path.dirname(_os.path.abspath(__file__)), '..'))
 import hashlib, json, os, sys
 import numpy as np, torch
 from capycrypt_b200 import Engine

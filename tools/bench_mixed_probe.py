@@ -1,5 +1,7 @@
 # development aid: BASELINE config 5 (mixed-size SHA3-512, log-uniform 64 B..1 MiB) device-resident probe.
 # usage: python bench_mixed_probe.py [total_GiB]
+import os as _os, sys as _sys
+_sys.path.insert(0, _os.path.join(_os.path.dirname(_os.path.abspath(__file__)), '..'))
 import json, sys
 import numpy as np, torch
 from capycrypt_b200 import Engine

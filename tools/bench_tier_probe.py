@@ -1,4 +1,6 @@
 # development aid: chain-bound batches through the tiered kernel vs one thread per message (CAPY_FLAG_NO_PAIR)
+import os as _os, sys as _sys
+_sys.path.insert(0, _os.path.join(_os.path.dirname(_os.path.abspath(__file__)), '..'))
 import json, os, sys
 import numpy as np, torch
 from capycrypt_b200 import Engine
