@@ -53,9 +53,11 @@ __device__ __forceinline__ void keccak_round_pair(uint32_t (&h)[25], uint32_t rc
 }
 #undef CAPY_PAIR_RHO_PI
 
-// both threads of the pair must call this together
+// both threads of the pair must call this together.  Four rounds per loop iteration: inside the sponge the loop
+// counter is not provably warp-uniform, so every iteration ends in a vector branch plus a convergence check in
+// front of the shuffles (~40 clocks at one warp per scheduler, where nothing hides them).
 __device__ __forceinline__ void keccak_f1600_pair(uint32_t (&h)[25], uint32_t half, unsigned mask = 0xffffffffu) {
-#pragma unroll 1
+#pragma unroll 4
   for (int r = 0; r < 24; r++) {
     const uint2 rc = KECCAK_RC[r];
     keccak_round_pair(h, half ? rc.y : rc.x, mask);
@@ -93,7 +95,8 @@ struct WarpKeccak {
   // all 32 threads of the warp together
   __device__ __forceinline__ void permute(uint32_t& lo, uint32_t& hi) const {
     const unsigned FULL = 0xffffffffu;
-#pragma unroll 1
+    // fully unrolled (24 x ~40 instructions = 16 KB): no loop branch, round constants become immediates
+#pragma unroll
     for (int r = 0; r < 24; r++) {
       const uint32_t clo = lop_xor3(lop_xor3(lo, __shfl_sync(FULL, lo, c1), __shfl_sync(FULL, lo, c2)), __shfl_sync(FULL, lo, c3), __shfl_sync(FULL, lo, c4));
       const uint32_t chi = lop_xor3(lop_xor3(hi, __shfl_sync(FULL, hi, c1), __shfl_sync(FULL, hi, c2)), __shfl_sync(FULL, hi, c3), __shfl_sync(FULL, hi, c4));

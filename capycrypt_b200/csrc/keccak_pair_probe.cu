@@ -129,7 +129,13 @@ int main(int argc, char** argv) {
       float ms4;
       cudaEventRecord(e0); chain_warp25_struct<<<blocks, 128>>>(d4, nperm, threads / 32, nullptr); cudaEventRecord(e1); cudaEventSynchronize(e1);
       cudaEventElapsedTime(&ms4, e0, e1);
-      printf("{\"warps_per_scheduler\": %d, \"warp25_struct_early_exit_us_per_perm\": %.4f}\n", wps, ms4 * 1e3 / nperm);
+      uint32_t* feed; cudaMalloc(&feed, (size_t)threads * (nperm + 1) * 4); cudaMemset(feed, 0x5a, (size_t)threads * (nperm + 1) * 4);
+      float ms5;
+      cudaEventRecord(e0); chain_warp25_struct<<<blocks, 128>>>(d4, nperm, threads / 32, feed); cudaEventRecord(e1); cudaEventSynchronize(e1);
+      cudaEventElapsedTime(&ms5, e0, e1);
+      cudaFree(feed);
+      printf("{\"warps_per_scheduler\": %d, \"warp25_struct_early_exit_us_per_perm\": %.4f, \"with_one_global_load_per_perm\": %.4f}\n", wps,
+             ms4 * 1e3 / nperm, ms5 * 1e3 / nperm);
       cudaFree(d4);
     }
     // pair kernel covers threads/2 items: compare those

@@ -256,12 +256,11 @@ struct LaunchPlan {
   uint64_t pair_items = 0;  // ranks [warp_items, warp_items + pair_items): two threads per item
 };
 
-// Measured on B200 at one warp per scheduler, per permutation of ONE chain: one thread per state 4.55 us; a thread
-// pair 3.35 us in isolation (csrc/keccak_pair_probe.cu) and 3.7-3.95 us inside the sponge (absorb loads, warp-uniform
-// step loop; 1 024 x 1 MiB SHA3-512: 53.6 ms against 67.0 ms); a whole warp per state 2.18 us in isolation and
-// 2.95 us inside the sponge (64 x 1 MiB: 43 ms against 67 ms).
-constexpr double kPairChainRatio = 3.95 / 4.6;
-constexpr double kWarpChainRatio = 3.0 / 4.6;
+// Measured on B200 at one warp per scheduler, per permutation of ONE chain (csrc/keccak_pair_probe.cu in isolation,
+// tools/bench_tier_probe.py inside the sponge on 1 MiB SHA3-512 messages): one thread per state 4.55 / 4.6 us; a thread
+// pair 2.93 / 3.55 us; a whole warp per state 2.18 / 2.19 us.
+constexpr double kPairChainRatio = 3.55 / 4.6;
+constexpr double kWarpChainRatio = 2.2 / 4.6;
 
 // Tiers of a chain-bound batch.  cum[k] = number of items in length bins > k (bin = whole blocks of the message).
 // Times are in units of one thread-per-state permutation; an SM hosts ONE block: 4 warp-tier, 64 pair-tier or 128

@@ -474,37 +474,39 @@ __device__ __noinline__ void sponge_item_warp(const SpongeJob& J, uint64_t i) { 
     lo = (uint32_t)v;
     hi = (uint32_t)(v >> 32);
   }
-  // whole-message blocks: this thread's lane as three aligned words + funnel shift, next block prefetched
+  // whole-message blocks: this thread's lane as three aligned words + funnel shift, next block prefetched.  Threads
+  // beyond the rate shadow lane 0 and mask their value away, so the hot loop has no divergent branch in front of the
+  // full-warp shuffles.
+  const uint32_t keep = mine ? 0xffffffffu : 0u;
   const uint8_t* p = g.x + (fb0 * STRIDE - g.x0) + 8ull * (mine ? l : 0);
   const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 3u) * 8u;
   const uint32_t* q = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)3);
   uint32_t w0 = 0, w1 = 0, w2 = 0;
-  if (fb0 < fb1 && mine) {
+  if (fb0 < fb1) {
     w0 = __ldg(q);
     w1 = __ldg(q + 1);
     w2 = sh != 0 ? __ldg(q + 2) : 0u;
   }
+  const uint64_t nblocks = g.nblocks, skip = J.skip_blocks;
 #pragma unroll 1
-  for (uint64_t b = J.skip_blocks; b < g.nblocks; b++) {
-    uint32_t vlo = 0, vhi = 0;
-    if (b >= fb0 && b < fb1) {
+  for (uint64_t b = skip; b < nblocks; b++) {
+    uint32_t vlo, vhi;
+    if (b >= fb0 && b < fb1) {  // warp-uniform: one item per warp
       vlo = __funnelshift_r(w0, w1, sh);
       vhi = __funnelshift_r(w1, w2, sh);
       q += 2 * LANES;
-      if (b + 1 < fb1 && mine) {
+      if (b + 1 < fb1) {
         w0 = __ldg(q);
         w1 = __ldg(q + 1);
         w2 = sh != 0 ? __ldg(q + 2) : 0u;
       }
-    } else if (mine) {
-      const uint64_t v = g.lane(b * STRIDE + 8ull * l);
+    } else {
+      const uint64_t v = g.lane(b * STRIDE + 8ull * (mine ? l : 0));
       vlo = (uint32_t)v;
       vhi = (uint32_t)(v >> 32);
     }
-    if (mine) {
-      lo ^= vlo;
-      hi ^= vhi;
-    }
+    lo ^= vlo & keep;
+    hi ^= vhi & keep;
     wk.permute(lo, hi);
   }
   // squeeze (sponge.rs:25-34, minus the dropped final permutation)
@@ -572,20 +574,23 @@ __device__ __noinline__ void sponge_item_pair_ool(const SpongeJob& J, uint64_t i
 }
 
 template <int LANES>
-__global__ void __launch_bounds__(128) sponge_tiered_kernel(const SpongeJob J, uint32_t warp_blocks, uint32_t pair_blocks) {
-  if (blockIdx.x < warp_blocks) {
-    const uint64_t r = (uint64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
-    if (r >= J.warp_items) return;  // whole warps leave together
-    sponge_item_warp<LANES>(J, sponge_rank_item(J, r));
-  } else if (blockIdx.x < warp_blocks + pair_blocks) {
+__global__ void __launch_bounds__(128, 1) sponge_tiered_kernel(const SpongeJob J, uint32_t warp_blocks, uint32_t pair_blocks) {
+  // __launch_bounds__(128, 1): with the default bound ptxas held the kernel at 128 registers and, once the unrolled
+  // warp-tier permutation was part of it, scheduled the (instruction-for-instruction identical) round loop of the
+  // thread tier differently: 5.4 instead of 4.6 us per permutation at one warp per scheduler.
+  if (blockIdx.x >= warp_blocks + pair_blocks) {
+    const uint64_t r = J.first + (uint64_t)(blockIdx.x - warp_blocks - pair_blocks) * blockDim.x + threadIdx.x;
+    if (r >= J.n) return;
+    sponge_item_solo_ool<LANES>(J, sponge_rank_item(J, r));
+  } else if (blockIdx.x >= warp_blocks) {
     const uint64_t t = (uint64_t)(blockIdx.x - warp_blocks) * blockDim.x + threadIdx.x;
     const uint64_t r = J.warp_items + (t >> 1);
     const bool valid = r < J.first;  // idle pairs of the last warp still take part in the shuffles
     sponge_item_pair_ool<LANES>(J, valid ? sponge_rank_item(J, r) : 0, valid, (uint32_t)(t & 1));
   } else {
-    const uint64_t r = J.first + (uint64_t)(blockIdx.x - warp_blocks - pair_blocks) * blockDim.x + threadIdx.x;
-    if (r >= J.n) return;
-    sponge_item_solo_ool<LANES>(J, sponge_rank_item(J, r));
+    const uint64_t r = (uint64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (r >= J.warp_items) return;  // whole warps leave together
+    sponge_item_warp<LANES>(J, sponge_rank_item(J, r));
   }
 }
 
