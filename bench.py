@@ -512,7 +512,7 @@ def extras(eng, dev, peaks, world, dist, rank):
         "scaling": "strong", "longest_chain_perms": int((lens.max() + 1 + 71) // 72),
         "ms_one_thread_per_message": ms_solo,
         "note": "a sponge is sequential per message: the step cannot be shorter than the longest message's chain "
-                "(1 MiB = 14 564 permutations: 67 ms with one thread per message, 54 ms with two threads, 43 ms with a "
+                "(1 MiB = 14 564 permutations: 67 ms with one thread per message, 52 ms with two threads, 32 ms with a "
                 "whole warp per message -- the tiers the longest messages of a chain-bound batch run in)"}
     del d5, o5, t_off5
 
