@@ -89,6 +89,20 @@ inline int stage_packed(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t st, int slot_
 
 constexpr uint64_t kChunkBytes = 8ull << 20;
 
+// Ragged batches: a chunk is one launch, and a launch cannot finish before the longest message in it has (a sponge
+// is sequential per message: ~30 ns per byte even with a whole warp on it), so a chunk that holds a long message must
+// also hold enough other work to fill the GPU for that time (~270 GB/s): at least ~8192 x the longest message.
+// Chunking a batch with 1 MiB messages into 8 MiB pieces made every piece chain-bound (measured: 6.9 s for 2.8 GiB).
+inline size_t chunk_count(uint64_t bytes, uint64_t items);
+inline size_t ragged_chunk_count(const uint64_t* off, uint64_t i0, uint64_t i1, uint64_t extra_bytes) {
+  uint64_t max_len = 0;
+  for (uint64_t i = i0; i < i1; i++) max_len = std::max<uint64_t>(max_len, off[i + 1] - off[i]);
+  const uint64_t bytes = off[i1] - off[i0] + extra_bytes;
+  const uint64_t min_chunk = std::max<uint64_t>(8ull << 20, 8192ull * max_len);
+  const size_t by_size = (size_t)std::max<uint64_t>(1, bytes / min_chunk);
+  return std::min<size_t>(by_size, chunk_count(bytes, i1 - i0));
+}
+
 inline size_t chunk_count(uint64_t bytes, uint64_t items) {
   uint64_t c = (bytes + kChunkBytes - 1) / kChunkBytes;
   c = std::max<uint64_t>(c, 1);

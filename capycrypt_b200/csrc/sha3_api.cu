@@ -672,9 +672,8 @@ int capy_sha3_batch(capy_ctx* ctx, int d_bits, const uint8_t* data, const uint64
   const size_t ob = (size_t)d_bits / 8;
   auto shards = split_items(off, 0, 0, n, ctx->devs.size(), 200);
   return for_each_device(ctx, shards, [&](DeviceCtx& dc, Range sh) -> int {
-    const uint64_t bytes = off[sh.i1] - off[sh.i0], items = sh.i1 - sh.i0;
-    // long messages: few big chunks, so that the longest-first schedule sees the whole shard
-    const size_t nchunks = bytes / items > 8192 ? (size_t)std::max<uint64_t>(1, bytes >> 31) : chunk_count(bytes, items);
+    // long messages: few big chunks, so that the longest-first schedule sees enough work beside them
+    const size_t nchunks = ragged_chunk_count(off, sh.i0, sh.i1, 0);
     auto chunks = split_items(off, 0, sh.i0, sh.i1, nchunks, 200);
     for (size_t c = 0; c < chunks.size(); c++) {
       const int s = (int)(c % kNumStreams);
@@ -753,7 +752,7 @@ int capy_cshake_batch(capy_ctx* ctx, int d_bits, const uint8_t* data, const uint
   auto shards = split_items(off, 0, 0, n, ctx->devs.size(), 200 + ob);
   return for_each_device(ctx, shards, [&](DeviceCtx& dc, Range sh) -> int {
     auto chunks = split_items(off, 0, sh.i0, sh.i1,
-                              chunk_count(off[sh.i1] - off[sh.i0] + (sh.i1 - sh.i0) * ob, sh.i1 - sh.i0), 200 + ob);
+                              ragged_chunk_count(off, sh.i0, sh.i1, (sh.i1 - sh.i0) * ob), 200 + ob);
     for (size_t c = 0; c < chunks.size(); c++) {
       const int s = (int)(c % kNumStreams);
       cudaStream_t st = dc.streams[s];
@@ -839,7 +838,7 @@ int capy_kmac_xof_batch(capy_ctx* ctx, int d_bits, const uint8_t* keys, const ui
   auto shards = split_items(off, 0, 0, n, ctx->devs.size(), 400 + ob);
   return for_each_device(ctx, shards, [&](DeviceCtx& dc, Range sh) -> int {
     const uint64_t tot = off[sh.i1] - off[sh.i0] + (out_begin(sh.i1) - out_begin(sh.i0));
-    auto chunks = split_items(off, 0, sh.i0, sh.i1, chunk_count(tot, sh.i1 - sh.i0), 400 + ob);
+    auto chunks = split_items(off, 0, sh.i0, sh.i1, ragged_chunk_count(off, sh.i0, sh.i1, tot - (off[sh.i1] - off[sh.i0])), 400 + ob);
     // 5 scratch slots per stream: data, off, keys, key_off, out (+ out_off)
     for (size_t c = 0; c < chunks.size(); c++) {
       const int s = (int)(c % kNumStreams);
