@@ -76,6 +76,28 @@ def test_var_base_edge_and_random(engine, oracle):
         assert got[i].tobytes() == E.point_to_bytes(E.scalar_mult(ks[i], E.point_from_bytes(ps[i]))), i
 
 
+def test_var_base_openssl_x448(engine):
+    """Independent pin of the variable-base path: RFC 7748 X448 shared secrets from OpenSSL equal y^2 / x^2 of the
+    engine's [k]P (edwards448 -> curve448 map of RFC 7748 4.2) for clamped scalars and random base points."""
+    x448 = pytest.importorskip("cryptography.hazmat.primitives.asymmetric.x448")
+    rnd = random.Random(33)
+    ks, pts, shared = [], [], []
+    for _ in range(32):
+        k = bytearray(rnd.randbytes(56))
+        base = E.scalar_mult(rnd.randrange(1, R), E.GENERATOR)
+        u = E.montgomery_u(base)
+        shared.append(x448.X448PrivateKey.from_private_bytes(bytes(k)).exchange(
+            x448.X448PublicKey.from_public_bytes(u.to_bytes(56, "little"))))
+        k[0] &= 252
+        k[55] |= 128
+        ks.append(int.from_bytes(k, "little"))
+        pts.append(E.point_to_bytes(base))
+    rc, got = engine.ed448_var_base(_be(ks), np.frombuffer(b"".join(pts), dtype=np.uint8))
+    assert rc == 0
+    for row, want in zip(got, shared):
+        assert E.montgomery_u(E.point_from_bytes(row.tobytes())).to_bytes(56, "little") == want
+
+
 def test_var_base_rejects_off_curve_points(engine):
     good = E.point_to_bytes(E.GENERATOR)
     bad = E.point_to_bytes((5, 7))
