@@ -643,6 +643,17 @@ using namespace capy;
 extern "C" {
 
 // =================================================================================================
+// diagnostics
+// =================================================================================================
+int capy_plan_tiers(const uint32_t* items_longer_than, uint32_t n_bins, uint64_t n, uint32_t max_blocks, uint64_t total_blocks,
+                    int sm_count, uint64_t* warp_items, uint64_t* pair_items) {
+  if (!items_longer_than || !n_bins || !warp_items || !pair_items || sm_count < 2) return CAPY_ERR_BAD_ARG;
+  std::vector<uint32_t> cum(items_longer_than, items_longer_than + n_bins);
+  plan_tiers(cum, n, max_blocks, (double)total_blocks, sm_count, warp_items, pair_items);
+  return CAPY_OK;
+}
+
+// =================================================================================================
 // SHA3-d
 // =================================================================================================
 int capy_sha3_batch_dev(capy_ctx* ctx, int dev_index, void* stream, int d_bits, const uint8_t* d_data,

@@ -75,6 +75,13 @@ void capy_host_free(void* p);
 /* number of kernels this ctx has launched so far (bench.py's gpu_launches evidence) */
 uint64_t capy_launch_count(const capy_ctx* ctx);
 
+/* ---- diagnostics: the host-side launch planner of chain-bound ragged sponge batches (no GPU needed) ------- */
+/* items_longer_than[k] = number of items whose message has MORE than k whole rate blocks (k < n_bins), n items,
+ * the longest with max_blocks blocks, total_blocks in all.  Returns how many of the longest items run with a whole
+ * warp per item and how many of the next with two threads per item (DESIGN.md "chain-bound batches"). */
+int capy_plan_tiers(const uint32_t* items_longer_than, uint32_t n_bins, uint64_t n, uint32_t max_blocks,
+                    uint64_t total_blocks, int sm_count, uint64_t* warp_items, uint64_t* pair_items);
+
 /* ---- SHA3-d : SpongeHashable::compute_sha3_hash (sha3/hashable.rs:19-21 -> shake,
  *      sha3/shake_functions.rs:24-32 -> sponge_absorb/squeeze, sha3/sponge.rs:10-34) ------- */
 /* digests: n * (d_bits/8) bytes, item-major.  Hashes the ORIGINAL bytes of every message (the

@@ -1,0 +1,76 @@
+"""CPU: the host-side launch planner of chain-bound sponge batches (csrc/sha3_api.cu plan_tiers, exported for tests as
+capy_plan_tiers).  No GPU needed: the planner is pure host logic over the length histogram.
+
+Model behind the expectations: one block per SM; a block carries 4 warp-tier, 64 pair-tier or 128
+thread-tier items; per permutation a thread-tier chain takes 1 unit, a pair 0.77, a warp 0.48."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from capycrypt_b200 import _binding as B
+
+NB = 1 << 14
+
+
+@pytest.fixture(scope="module")
+def lib():
+    return B.load()
+
+
+def plan(lib, lens_blocks, sm=148):
+    lens_blocks = np.asarray(lens_blocks, dtype=np.int64)
+    bins = np.minimum(lens_blocks, NB - 1)
+    hist = np.bincount(bins, minlength=NB)
+    longer = (len(bins) - np.cumsum(hist)).astype(np.uint32)  # items in bins > k
+    w, p = C.c_uint64(), C.c_uint64()
+    rc = lib.capy_plan_tiers(longer.ctypes.data, NB, len(bins), int(bins.max()) + 1, int((bins + 1).sum()), sm,
+                             C.addressof(w), C.addressof(p))
+    assert rc == 0
+    return int(w.value), int(p.value)
+
+
+def test_single_long_message_gets_a_warp(lib):
+    assert plan(lib, [58254]) == (1, 0)          # 1 x 4 MiB of SHA3-512
+    assert plan(lib, [14563] * 64) == (64, 0)    # 64 x 1 MiB: 16 blocks of 4 warps
+
+
+def test_many_equal_long_messages_prefer_the_pair_tier_when_warps_do_not_fit(lib):
+    w, p = plan(lib, [14563] * 1024)             # 256 warp blocks would not fit 148 SMs
+    assert w == 0 and p == 1024
+
+
+def test_work_bound_batch_has_no_fast_tier(lib):
+    rng = np.random.default_rng(1)
+    # 2^20 short messages: the longest chain is nowhere near the work-bound time (the C side would not even call the
+    # planner here; called directly it must still return an empty plan)
+    assert plan(lib, rng.integers(0, 20, size=1 << 20)) == (0, 0)
+
+
+def _mixed(total_bytes, seed=5):
+    rs = np.random.default_rng(seed)
+    lens, acc = [], 0
+    while acc < total_bytes:
+        c = np.exp(rs.uniform(np.log(64), np.log(1 << 20), size=8192)).astype(np.int64)
+        lens.append(c)
+        acc += int(c.sum())
+    lens = np.concatenate(lens)
+    return lens[: int(np.searchsorted(np.cumsum(lens), total_bytes)) + 1] // 72
+
+
+def test_mixed_batches_like_config_5(lib):
+    # 16 GiB: almost work-bound -> a pair tier of about a thousand items, no warp tier
+    w, p = plan(lib, _mixed(16 << 30))
+    assert w == 0 and 500 <= p <= 3000
+    # the 2 GiB shard of an 8-GPU run: chain-bound -> both fast tiers, all of their blocks resident at once
+    w, p = plan(lib, _mixed(2 << 30))
+    assert w > 0 and p > 0 and (w + 3) // 4 + (p + 63) // 64 < 148
+    # every chain must fit the step the planner assumed: the first thread-tier item is shorter than the first pair item
+    # times 0.77 / 1 and the first pair item shorter than the longest times 0.48 / 0.77
+    lens = np.sort(_mixed(2 << 30))[::-1] + 1
+    assert lens[w + p] <= lens[w] and lens[w] * 0.772 >= lens[0] * 0.478 * 0.99
+
+
+def test_bad_arguments(lib):
+    w, p = C.c_uint64(), C.c_uint64()
+    assert lib.capy_plan_tiers(None, NB, 1, 1, 1, 148, C.addressof(w), C.addressof(p)) == B.ERR_BAD_ARG
