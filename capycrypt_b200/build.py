@@ -31,7 +31,7 @@ PER_SOURCE_DEFINES = {"ed448_var.cu": ["-DCAPY_FE_OOL", "-DCAPY_VB_HOT_INLINE", 
 NVCC = os.environ.get("NVCC", "nvcc")
 BASE_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC,-O3,-Wall", "--expt-relaxed-constexpr",
+    "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unknown-pragmas", "--expt-relaxed-constexpr",
 ]
 
 

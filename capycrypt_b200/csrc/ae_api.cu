@@ -397,7 +397,7 @@ int capy_sponge_encrypt_batch(capy_ctx* ctx, int d_bits, int variant, const uint
     cudaStream_t st = dc.streams[0];
     const uint64_t cnt = sh.i1 - sh.i0;
     StagedPacked sp, sm;
-    uint8_t* d_nonce;
+    uint8_t* d_nonce = nullptr;
     int rc = stage_packed(ctx, dc, st, SA_H0, SA_H0 + 1, pws, pw_off, sh.i0, sh.i1, &sp);
     if (rc) return rc;
     rc = stage_packed(ctx, dc, st, SA_H0 + 2, SA_H0 + 3, msgs, msg_off, sh.i0, sh.i1, &sm);
@@ -433,7 +433,7 @@ int capy_sponge_decrypt_batch(capy_ctx* ctx, int d_bits, int variant, const uint
     cudaStream_t st = dc.streams[0];
     const uint64_t cnt = sh.i1 - sh.i0;
     StagedPacked sp, sc;
-    uint8_t *d_nonce, *d_tag;
+    uint8_t *d_nonce = nullptr, *d_tag = nullptr;
     int rc = stage_packed(ctx, dc, st, SA_H0, SA_H0 + 1, pws, pw_off, sh.i0, sh.i1, &sp);
     if (rc) return rc;
     rc = stage_packed(ctx, dc, st, SA_H0 + 2, SA_H0 + 3, ct, ct_off, sh.i0, sh.i1, &sc);
@@ -492,7 +492,7 @@ int capy_ed448_key_encrypt_batch(capy_ctx* ctx, int d_bits, const uint8_t* pub_x
     cudaStream_t st = dc.streams[0];
     const uint64_t cnt = sh.i1 - sh.i0;
     StagedPacked sm;
-    uint8_t *d_pub, *d_k;
+    uint8_t *d_pub = nullptr, *d_k = nullptr;
     int rc = stage_packed(ctx, dc, st, SA_H0, SA_H0 + 1, msgs, msg_off, sh.i0, sh.i1, &sm);
     if (rc) return rc;
     rc = h2d_fixed(ctx, dc, st, SA_H0 + 2, pub_xy112 + 112 * sh.i0, (size_t)cnt * 112, &d_pub);
@@ -534,7 +534,7 @@ int capy_ed448_key_decrypt_batch(capy_ctx* ctx, int d_bits, const uint8_t* pws, 
     cudaStream_t st = dc.streams[0];
     const uint64_t cnt = sh.i1 - sh.i0;
     StagedPacked sp, sc;
-    uint8_t *d_z, *d_tag;
+    uint8_t *d_z = nullptr, *d_tag = nullptr;
     int rc = stage_packed(ctx, dc, st, SA_H0, SA_H0 + 1, pws, pw_off, sh.i0, sh.i1, &sp);
     if (rc) return rc;
     rc = stage_packed(ctx, dc, st, SA_H0 + 2, SA_H0 + 3, ct, ct_off, sh.i0, sh.i1, &sc);

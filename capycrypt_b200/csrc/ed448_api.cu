@@ -377,7 +377,7 @@ int capy_ed448_fixed_base_batch(capy_ctx* ctx, const uint8_t* scalars_be56, uint
   return for_each_device(ctx, shards, [&](DeviceCtx& dc, Range sh) -> int {
     cudaStream_t st = dc.streams[0];
     const uint64_t cnt = sh.i1 - sh.i0;
-    uint8_t *d_sc, *d_out;
+    uint8_t *d_sc = nullptr, *d_out = nullptr;
     int rc = h2d(ctx, dc, st, SL_H_IN0, scalars_be56 + 56 * sh.i0, cnt * 56, &d_sc);
     if (rc) return rc;
     d_out = (uint8_t*)scratch_get(dc, SL_H_IN0 + 1, cnt * 112);
@@ -400,7 +400,7 @@ int capy_ed448_var_base_batch(capy_ctx* ctx, const uint8_t* scalars_be56, const 
   int rc = for_each_device(ctx, shards, [&](DeviceCtx& dc, Range sh) -> int {
     cudaStream_t st = dc.streams[0];
     const uint64_t cnt = sh.i1 - sh.i0;
-    uint8_t *d_sc, *d_pt;
+    uint8_t *d_sc = nullptr, *d_pt = nullptr;
     int rc = h2d(ctx, dc, st, SL_H_IN0, scalars_be56 + 56 * sh.i0, cnt * 56, &d_sc);
     if (rc) return rc;
     rc = h2d(ctx, dc, st, SL_H_IN0 + 1, points_xy112 + 112 * sh.i0, cnt * 112, &d_pt);
@@ -482,7 +482,7 @@ int capy_ed448_verify_batch(capy_ctx* ctx, int d_bits, const uint8_t* pub_xy112,
     cudaStream_t st = dc.streams[0];
     const uint64_t cnt = sh.i1 - sh.i0;
     StagedPacked sm;
-    uint8_t *d_pub, *d_h, *d_z;
+    uint8_t *d_pub = nullptr, *d_h = nullptr, *d_z = nullptr;
     int rc = stage_packed(ctx, dc, st, SL_H_IN0, SL_H_IN0 + 1, msgs, msg_off, sh.i0, sh.i1, &sm);
     if (rc) return rc;
     rc = h2d(ctx, dc, st, SL_H_IN0 + 2, pub_xy112 + 112 * sh.i0, cnt * 112, &d_pub);
@@ -516,7 +516,7 @@ int capy_ed448_ecdh_batch(capy_ctx* ctx, const uint8_t* k_rand56, const uint8_t*
   int rc = for_each_device(ctx, shards, [&](DeviceCtx& dc, Range sh) -> int {
     cudaStream_t st = dc.streams[0];
     const uint64_t cnt = sh.i1 - sh.i0;
-    uint8_t *d_k, *d_pub;
+    uint8_t *d_k = nullptr, *d_pub = nullptr;
     int rc = h2d(ctx, dc, st, SL_H_IN0, k_rand56 + 56 * sh.i0, cnt * 56, &d_k);
     if (rc) return rc;
     rc = h2d(ctx, dc, st, SL_H_IN0 + 1, pub_xy112 + 112 * sh.i0, cnt * 112, &d_pub);

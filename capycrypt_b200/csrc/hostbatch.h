@@ -69,8 +69,8 @@ inline int for_each_device(capy_ctx* ctx, const std::vector<Range>& shards, F&& 
 
 // one packed host input staged per chunk: bytes [a0, off[i1]) with a0 = off[i0] rounded down to 16
 struct StagedPacked {
-  const uint8_t* d_base;  // device pointer such that d_base + off[i] addresses item i
-  const uint64_t* d_off;  // device copy of off[i0 .. i1]
+  const uint8_t* d_base = nullptr;  // device pointer such that d_base + off[i] addresses item i
+  const uint64_t* d_off = nullptr;  // device copy of off[i0 .. i1]
 };
 
 inline int stage_packed(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t st, int slot_data, int slot_off, const uint8_t* data,

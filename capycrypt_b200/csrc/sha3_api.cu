@@ -175,7 +175,6 @@ __global__ void len_hist_kernel(const uint64_t* __restrict__ off, uint64_t n, ui
 // (lo, hi), max bin, number of non-empty bins}.  1024 threads x 16 consecutive bins (four 128-bit loads each),
 // thread 0 owns the HIGHEST bins.
 __global__ void __launch_bounds__(1024) len_scan_kernel(uint32_t* hist, uint32_t* summary) {
-  __shared__ uint32_t part[1024];
   __shared__ unsigned long long tot_s;
   __shared__ uint32_t max_s, bins_s;
   const uint32_t t = threadIdx.x;
@@ -198,14 +197,13 @@ __global__ void __launch_bounds__(1024) len_scan_kernel(uint32_t* hist, uint32_t
     if (c[k]) { nb++; mx = lo + k; }  // ascending k: the last non-empty one is the largest
     tot += (unsigned long long)c[k] * (lo + k + 1);
   }
-  part[t] = sum;
   if (sum) {
     atomicAdd(&tot_s, tot);
     atomicMax(&max_s, mx);
     atomicAdd(&bins_s, nb);
   }
   __syncthreads();
-  // inclusive scan of part[] over the threads (thread 0 = highest bins): warp shuffles, then the 32 warp totals
+  // inclusive scan of the per-thread sums over the threads (thread 0 = highest bins): warp shuffles, then the 32 warp totals
   uint32_t incl = sum;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
