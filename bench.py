@@ -476,6 +476,23 @@ def extras(eng, dev, peaks, world, dist, rank):
         "GBps": world * n2 * mlen / (ms * 1e-3) / 1e9, "ms_per_step": ms,
         "frac_int_alu": n2 * perms * OPS_PER_PERM / (ms * 1e-3) / peaks["lop3"], "perms_per_msg": perms}
 
+    # cfg 2, variable-length squeeze: cSHAKE256 and KMACXOF256 with a 4 096-byte output per message (the keystream shape of
+    # sha3/encryptable.rs:41), and FIPS 202 SHAKE256 (no reference counterpart) with a 64-byte output
+    off2 = torch.arange(n2 + 1, dtype=torch.int64, device=dev) * mlen
+    koff2 = torch.arange(n2 + 1, dtype=torch.int64, device=dev) * 32
+    big = torch.zeros(n2 * 4096, dtype=torch.uint8, device=dev)
+    ms_c = timed(lambda: eng.cshake_dev(data, off2, 8 * 4096, b"", b"Email Signature", 512, big), 5)
+    ms_k = timed(lambda: eng.kmac_xof_dev(keys, koff2, data, off2, 8 * 4096, b"My Tagged Application", 512, big), 5)
+    ms_s = timed(lambda: eng.fips_shake_dev(data, off2, 256, 64, o), 5)
+    sq = (4096 + 135) // 136 - 1  # extra permutations of a 4 096-byte squeeze at rate 136
+    out["cfg2_variable_squeeze_2^16x4KB"] = {
+        "cshake256_out4096B_ms": ms_c, "cshake256_out4096B_GBps_in_plus_out": world * n2 * (mlen + 4096) / (ms_c * 1e-3) / 1e9,
+        "cshake256_frac_int_alu": n2 * (31 + sq) * OPS_PER_PERM / (ms_c * 1e-3) / peaks["lop3"],
+        "kmacxof256_out4096B_ms": ms_k, "kmacxof256_frac_int_alu": n2 * (32 + sq) * OPS_PER_PERM / (ms_k * 1e-3) / peaks["lop3"],
+        "fips_shake256_out64B_ms": ms_s, "fips_shake256_GBps": world * n2 * mlen / (ms_s * 1e-3) / 1e9,
+        "fips_shake256_frac_int_alu": n2 * 31 * OPS_PER_PERM / (ms_s * 1e-3) / peaks["lop3"]}
+    del big
+
     # cfg 5: mixed-size SHA3-512, lengths log-uniform in [64 B, 1 MiB], 16 GiB in total (strong scaling: the
     # 16 GiB are split over the ranks); longest-message-first schedule, one thread per message
     import numpy as np
