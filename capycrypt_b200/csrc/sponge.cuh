@@ -323,6 +323,26 @@ __device__ __forceinline__ void sponge_item(const SpongeJob& J, uint64_t i) {
   const uint8_t* xi = J.xor_in ? J.xor_in + (o - J.out) : nullptr;
   const bool o_aligned = (reinterpret_cast<uintptr_t>(o) & 7u) == 0 && (!xi || (reinterpret_cast<uintptr_t>(xi) & 7u) == 0);
   for (uint64_t produced = 0; produced < out_bytes;) {
+    if (o_aligned && produced + sq_bytes <= out_bytes) {
+      // whole squeeze block, 8-byte aligned: straight stores (the keystream / long-output shape)
+      uint2* op = reinterpret_cast<uint2*>(o + produced);
+      const uint2* xp = reinterpret_cast<const uint2*>(xi ? xi + produced : nullptr);
+#pragma unroll
+      for (int j = 0; j < 21; j++) {
+        if (j < (int)J.sq_lanes) {
+          uint2 v = make_uint2(a[j].lo, a[j].hi);
+          if (xi) {
+            const uint2 m = xp[j];
+            v.x ^= m.x;
+            v.y ^= m.y;
+          }
+          op[j] = v;
+        }
+      }
+      produced += sq_bytes;
+      if (produced < out_bytes) keccak_f1600(a);
+      continue;
+    }
 #pragma unroll
     for (int j = 0; j < 21; j++) {
       const uint64_t pos = produced + 8ull * j;
