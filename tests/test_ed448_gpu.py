@@ -76,6 +76,26 @@ def test_var_base_edge_and_random(engine, oracle):
         assert got[i].tobytes() == E.point_to_bytes(E.scalar_mult(ks[i], E.point_from_bytes(ps[i]))), i
 
 
+@pytest.mark.parametrize("n", [1, 2, 31, 127, 128, 129, 257])
+def test_odd_batch_sizes_hit_the_partial_last_block(engine, oracle, n):
+    """The curve kernels keep idle threads of the last block in the loops (block barriers): batch sizes around the block
+    size must neither hang nor touch memory past the batch."""
+    rnd = random.Random(500 + n)
+    sc = _be([rnd.randrange(2**448) for _ in range(n)])
+    fixed = engine.ed448_fixed_base(sc)
+    assert np.array_equal(fixed, oracle.fixed_base_batch(sc, threads=0))
+    rc, var = engine.ed448_var_base(sc, fixed.reshape(-1))
+    rc2, want = oracle.var_base_batch(sc, fixed.reshape(-1), threads=0)
+    assert rc == rc2 == 0 and np.array_equal(var, want)
+    pws, po = pack([rnd.randbytes(rnd.randrange(0, 40)) for _ in range(n)])
+    md, mo = pack([rnd.randbytes(rnd.randrange(0, 300)) for _ in range(n)])
+    h, z = engine.ed448_sign(pws, po, md, mo, 256)
+    ho, zo = oracle.sign_batch(pws, po, md, mo, 256, threads=0)
+    assert np.array_equal(h, ho) and np.array_equal(z, zo)
+    rc, ok = engine.ed448_verify(engine.ed448_keygen(pws, po, 256), md, mo, h, z, 256)
+    assert rc == 0 and ok.all()
+
+
 def test_var_base_openssl_x448(engine):
     """Independent pin of the variable-base path: RFC 7748 X448 shared secrets from OpenSSL equal y^2 / x^2 of the
     engine's [k]P (edwards448 -> curve448 map of RFC 7748 4.2) for clamped scalars and random base points."""
