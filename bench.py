@@ -567,6 +567,23 @@ def extras(eng, dev, peaks, world, dist, rank):
     out["ed448_schnorr_2^18x256B"] = {
         "keygens_per_s": world * n4 / (ms_k * 1e-3), "signs_per_s": world * n4 / (ms_s * 1e-3),
         "verifies_per_s": world * n4 / (ms_v * 1e-3), "ms_keygen": ms_k, "ms_sign": ms_s, "ms_verify": ms_v}
+    # the other message sizes SURVEY 8(d) asks for (64 B and 4 KB) and cfg 3's password variant (2^20 x 32-byte passwords)
+    for mlen4 in (64, 4096):
+        msg_b = rnd(n4 * mlen4)
+        off_b = torch.arange(n4 + 1, dtype=torch.int64, device=dev) * mlen4
+        ms_s2 = timed(lambda: eng.ed448_sign_dev(pw, pw_off, msg_b, off_b, 512, h, z), 2, 1)
+        ms_v2 = timed(lambda: eng.ed448_verify_dev(pub, msg_b, off_b, h, z, 512, ok), 2, 1)
+        assert bool(ok.all().item())
+        out[f"ed448_schnorr_2^18x{mlen4}B"] = {"signs_per_s": world * n4 / (ms_s2 * 1e-3), "verifies_per_s": world * n4 / (ms_v2 * 1e-3),
+                                               "ms_sign": ms_s2, "ms_verify": ms_v2}
+        del msg_b, off_b
+    pw20 = rnd(n3 * 32)
+    pw20_off = torch.arange(n3 + 1, dtype=torch.int64, device=dev) * 32
+    pub20 = torch.zeros(n3 * 112, dtype=torch.uint8, device=dev)
+    ms_k20 = timed(lambda: eng.ed448_keygen_dev(pw20, pw20_off, 512, pub20), 2, 1)
+    out["ed448_keygen_2^20_passwords"] = {"keygens_per_s": world * n3 / (ms_k20 * 1e-3), "ms_per_step": ms_k20}
+    del pw20, pw20_off, pub20
+    eng.ed448_sign_dev(pw, pw_off, msg, msg_off, 512, h, z)  # h, z back to the 256-byte messages for what follows
 
     # "next" rows N2 / N3: sponge AE over the cfg-2 shape (2^16 x 4 KB: two 4 KB KMAC passes per message,
     # one absorbing, one squeezing into the XOR) and ECDHIES over 2^17 x 256 B, device-resident
