@@ -33,6 +33,7 @@ SIGNATURES = {
     "capy_gpu_init": (i32, [C.POINTER(C.c_int), i32, C.POINTER(vp)]),
     "capy_gpu_destroy": (None, [vp]),
     "capy_gpu_device_count": (i32, [vp]),
+    "capy_gpu_scrub": (i32, [vp]),
     "capy_strerror": (C.c_char_p, [i32]),
     "capy_last_cuda_error": (C.c_char_p, [vp]),
     "capy_version": (i32, []),

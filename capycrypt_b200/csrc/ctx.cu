@@ -123,6 +123,19 @@ void capy_gpu_destroy(capy_ctx* ctx) {
   delete ctx;
 }
 
+int capy_gpu_scrub(capy_ctx* ctx) {
+  if (!ctx) return CAPY_ERR_BAD_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  for (DeviceCtx& dc : ctx->devs) {
+    DeviceGuard g(dc.dev);
+    CAPY_CUDA(ctx, cudaDeviceSynchronize());
+    for (Scratch& sc : dc.scratch)
+      if (sc.p) CAPY_CUDA(ctx, cudaMemset(sc.p, 0, sc.cap));
+    CAPY_CUDA(ctx, cudaDeviceSynchronize());
+  }
+  return CAPY_OK;
+}
+
 int capy_gpu_device_count(const capy_ctx* ctx) { return ctx ? (int)ctx->devs.size() : 0; }
 
 const char* capy_last_cuda_error(const capy_ctx* ctx) { return ctx ? ctx->last_cuda_error.c_str() : ""; }

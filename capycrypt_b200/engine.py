@@ -75,6 +75,10 @@ class Engine:
         except Exception:
             pass
 
+    def scrub(self):
+        """zero every device scratch buffer of the ctx (intermediate secrets of the pipelines live there)"""
+        self._check(self.lib.capy_gpu_scrub(self._ctx))
+
     # ---- plumbing ----
     def _check(self, rc: int, allow=()):
         if rc != B.OK and rc not in allow:

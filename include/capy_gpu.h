@@ -65,6 +65,10 @@ typedef struct capy_ctx capy_ctx;
 int capy_gpu_init(const int* devices, int n_devices, capy_ctx** out_ctx);
 void capy_gpu_destroy(capy_ctx* ctx);
 int capy_gpu_device_count(const capy_ctx* ctx);
+/* Overwrites every device scratch buffer of the ctx with zeros.  The pipelines keep intermediate secrets there
+ * (derived scalars, KMAC key material, staged passwords) until the next call reuses the buffer; the reference does
+ * not zeroize either, so this is an extra for callers who want it.  Blocking. */
+int capy_gpu_scrub(capy_ctx* ctx);
 const char* capy_strerror(int status);
 /* last CUDA error text seen by this ctx (for CAPY_ERR_CUDA) */
 const char* capy_last_cuda_error(const capy_ctx* ctx);

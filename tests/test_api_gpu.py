@@ -64,3 +64,16 @@ def test_sign_verify_like_test_sig_512(gpu):
     assert all(r is not None and r.kind == "SignatureVerificationFailure" for r in res)
     res = gpu.verify([Message.new(b"x")], [keys[0].pub_key])
     assert res[0].kind == "SignatureNotSet"
+
+
+def test_scrub_keeps_the_ctx_usable(gpu):
+    """capy_gpu_scrub zeroes the device scratch (intermediate secrets); the next calls must work and agree."""
+    m = [Message.new(b"abc"), Message.new(b"")]
+    gpu.compute_sha3_hash(m, SecParam.D256)
+    first = [x.digest for x in m]
+    keys = gpu.new_keypairs([b"pw1", b"pw2"], "k", SecParam.D512)
+    gpu.engine.scrub()
+    m2 = [Message.new(b"abc"), Message.new(b"")]
+    gpu.compute_sha3_hash(m2, SecParam.D256)
+    assert [x.digest for x in m2] == first
+    assert [k.pub_key for k in gpu.new_keypairs([b"pw1", b"pw2"], "k", SecParam.D512)] == [k.pub_key for k in keys]
