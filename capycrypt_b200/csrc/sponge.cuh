@@ -382,11 +382,13 @@ __device__ __forceinline__ void sponge_item_pair(const SpongeJob& J, uint64_t i,
   uint8_t* o = nullptr;
   const uint8_t* xi = nullptr;
   uint64_t out_bytes = 0;
-  const uint64_t sq_bytes = 8ull * J.sq_lanes;
+  const uint32_t sq_lanes = J.sq_lanes;  // (J lives in memory behind a reference: keep what the step loop needs in registers)
+  const uint64_t skip = J.skip_blocks;
+  const uint64_t sq_bytes = 8ull * sq_lanes;
   if (valid) {
     g.init(J, i);
-    g.fast_range(STRIDE, J.skip_blocks, fb0, fb1);
-    n_absorb = g.nblocks - J.skip_blocks;
+    g.fast_range(STRIDE, skip, fb0, fb1);
+    n_absorb = g.nblocks - skip;
     if (J.out_off) {
       o = J.out + J.out_off[i];
       out_bytes = J.out_off[i + 1] - J.out_off[i];
@@ -429,7 +431,7 @@ __device__ __forceinline__ void sponge_item_pair(const SpongeJob& J, uint64_t i,
 #pragma unroll
     for (int j = 0; j < 21; j++) {
       const uint64_t hp = produced + 8ull * j + 4ull * half;  // this thread's four bytes of lane j
-      if (j < (int)J.sq_lanes && hp < out_bytes) {
+      if (j < (int)sq_lanes && hp < out_bytes) {
         if (o_aligned && hp + 4 <= out_bytes) {
           uint32_t v = h[j];
           if (xi) v ^= *reinterpret_cast<const uint32_t*>(xi + hp);
@@ -444,7 +446,7 @@ __device__ __forceinline__ void sponge_item_pair(const SpongeJob& J, uint64_t i,
 #pragma unroll 1
   for (uint64_t s = 0; s <= warp_steps; s++) {
     if (s < n_absorb) {
-      const uint64_t b = J.skip_blocks + s;
+      const uint64_t b = skip + s;
       if (b >= fb0 && b < fb1) {
 #pragma unroll
         for (int j = 0; j < LANES; j++) h[j] ^= __funnelshift_r(c0[j], c1[j], sh);
