@@ -24,6 +24,43 @@ __global__ void __launch_bounds__(128) chain_pair(uint64_t* st, int nperm) {
   for (int k = 0; k < 25; k++) o[((size_t)item * 25 + k) * 2 + half] = h[k];
 }
 
+// the pair chain with an absorb in front of every permutation: 9 words per thread from a per-pair stream (pairs of a warp
+// read 16 different streams, like 16 different messages), next block prefetched -- MODE 0: 32-bit loads of the own halves,
+// MODE 1: one 64-bit load per lane by alternating threads + exchange of the foreign halves by shuffle
+template <int MODE>
+__global__ void __launch_bounds__(128) chain_pair_feed(uint64_t* st, int nperm, const uint32_t* __restrict__ feed, size_t stream_words) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int item = t >> 1;
+  const uint32_t half = t & 1;
+  uint32_t h[25];
+  for (int k = 0; k < 25; k++) { uint64_t v = st[(size_t)item * 25 + k]; h[k] = half ? (uint32_t)(v >> 32) : (uint32_t)v; }
+  const uint32_t* q = feed + (size_t)item * stream_words;
+  uint32_t c[9];
+  uint2 d[5];
+  if (MODE == 0) { for (int j = 0; j < 9; j++) c[j] = __ldg(q + 2 * j + half); }
+  else { for (int j = 0; j < 5; j++) if (2 * j + (int)half < 9) d[j] = __ldg(reinterpret_cast<const uint2*>(q) + 2 * j + half); }
+  for (int p = 0; p < nperm; p++) {
+    if (MODE == 0) {
+      for (int j = 0; j < 9; j++) h[j] ^= c[j];
+      q += 18;
+      for (int j = 0; j < 9; j++) c[j] = __ldg(q + 2 * j + half);
+    } else {
+      // thread `half` holds lanes 2j + half entirely; it keeps its own half and hands the other half to the partner
+      for (int j = 0; j < 5; j++) {
+        const uint32_t mine = half ? d[j].y : d[j].x, theirs = half ? d[j].x : d[j].y;
+        const uint32_t got = __shfl_xor_sync(0xffffffffu, theirs, 1);  // partner's lane 2j + (1 - half), my half of it
+        if (2 * j + (int)half < 9) h[2 * j + half] ^= mine;
+        if (2 * j + 1 - (int)half < 9) h[2 * j + 1 - half] ^= got;
+      }
+      q += 18;
+      for (int j = 0; j < 5; j++) if (2 * j + (int)half < 9) d[j] = __ldg(reinterpret_cast<const uint2*>(q) + 2 * j + half);
+    }
+    keccak_f1600_pair(h, half);
+  }
+  uint32_t* o = reinterpret_cast<uint32_t*>(st);
+  for (int k = 0; k < 25; k++) o[((size_t)item * 25 + k) * 2 + half] = h[k];
+}
+
 // one state per warp: thread l < 25 owns lane l = x + 5y
 __constant__ uint8_t RHO25[25] = {0, 1, 62, 28, 27, 36, 44, 6, 55, 20, 3, 10, 43, 25, 39, 41, 45, 15, 21, 8, 18, 2, 61, 56, 14};
 __global__ void __launch_bounds__(128) chain_warp25(uint64_t* st, int nperm) {
@@ -137,6 +174,25 @@ int main(int argc, char** argv) {
       printf("{\"warps_per_scheduler\": %d, \"warp25_struct_early_exit_us_per_perm\": %.4f, \"with_one_global_load_per_perm\": %.4f}\n", wps,
              ms4 * 1e3 / nperm, ms5 * 1e3 / nperm);
       cudaFree(d4);
+    }
+    if (wps == 1) {
+      const size_t stream_words = (size_t)18 * (nperm + 2);
+      uint32_t* feed; cudaMalloc(&feed, (size_t)(threads / 2) * stream_words * 4); cudaMemset(feed, 0x3c, (size_t)(threads / 2) * stream_words * 4);
+      uint64_t *d5, *d6; cudaMalloc(&d5, init.size() * 8); cudaMalloc(&d6, init.size() * 8);
+      cudaMemcpy(d5, init.data(), init.size() * 8, cudaMemcpyHostToDevice);
+      cudaMemcpy(d6, init.data(), init.size() * 8, cudaMemcpyHostToDevice);
+      float m0, m1;
+      chain_pair_feed<0><<<blocks, 128>>>(d5, 2, feed, stream_words); chain_pair_feed<1><<<blocks, 128>>>(d6, 2, feed, stream_words);
+      cudaEventRecord(e0); chain_pair_feed<0><<<blocks, 128>>>(d5, nperm, feed, stream_words); cudaEventRecord(e1); cudaEventSynchronize(e1);
+      cudaEventElapsedTime(&m0, e0, e1);
+      cudaEventRecord(e0); chain_pair_feed<1><<<blocks, 128>>>(d6, nperm, feed, stream_words); cudaEventRecord(e1); cudaEventSynchronize(e1);
+      cudaEventElapsedTime(&m1, e0, e1);
+      std::vector<uint64_t> r5(init.size()), r6(init.size());
+      cudaMemcpy(r5.data(), d5, r5.size() * 8, cudaMemcpyDeviceToHost); cudaMemcpy(r6.data(), d6, r6.size() * 8, cudaMemcpyDeviceToHost);
+      size_t bad56 = 0; for (size_t i = 0; i < (size_t)threads / 2 * 25; i++) bad56 += r5[i] != r6[i];
+      printf("{\"pair_with_absorb_us_per_perm\": {\"own_halves_32bit_loads\": %.4f, \"whole_lanes_64bit_loads_plus_exchange\": %.4f}, \"variants_agree\": %s, \"err\": \"%s\"}\n",
+             m0 * 1e3 / nperm, m1 * 1e3 / nperm, bad56 ? "false" : "true", cudaGetErrorString(cudaGetLastError()));
+      cudaFree(feed); cudaFree(d5); cudaFree(d6);
     }
     // pair kernel covers threads/2 items: compare those
     std::vector<uint64_t> r1((size_t)threads * 25), r2((size_t)threads * 25);
