@@ -72,3 +72,34 @@ def test_fuzz_kmac_variable_output_lengths(engine, oracle):
                                          data[int(off[i]):int(off[i + 1])], np.array([0, off[i + 1] - off[i]], np.uint64),
                                          8 * outs[i], b"SKE", d, threads=1)[0] if outs[i] else np.zeros(0, np.uint8)
             assert np.array_equal(got[int(out_off[i]):int(out_off[i + 1])], want), (d, i, outs[i])
+
+
+@pytest.mark.parametrize("d", [224, 256, 384, 512])
+def test_fuzz_sponge_ae_against_kmac_oracle(engine, oracle, d):
+    """sha3_encrypt / sha3_decrypt (sha3/encryptable.rs:29-83) for a few hundred ragged items, the expected values composed
+    from the C oracle's KMACXOF: (ke || ka) = KMACXOF(z || pw, "", 1024, "S"), t = KMACXOF(ka, m, 512, "SKA"),
+    c = KMACXOF(ke, "", |m|, "SKE") xor m."""
+    rng = np.random.default_rng(4000 + d)
+    n = 300
+    msgs = _items(rng, n)
+    pws = _items(rng, n, long_ok=False)
+    nonces = [bytes(rng.integers(0, 256, size=512, dtype=np.uint8)) for _ in range(n)]
+    md, mo = pack(msgs)
+    pd, po = pack(pws)
+    ct, tag = engine.sponge_encrypt(pd, po, b"".join(nonces), 512, md, mo, d)
+    kd, ko = pack([z + p for z, p in zip(nonces, pws)])
+    empty = np.zeros(n + 1, np.uint64)
+    none = np.zeros(0, np.uint8)
+    ke_ka = oracle.kmac_xof_batch(kd, ko, none, empty, 1024, b"S", d, threads=0)
+    ka, kao = pack([r[64:].tobytes() for r in ke_ka])
+    want_tag = oracle.kmac_xof_batch(ka, kao, md, mo, 512, b"SKA", d, threads=0)
+    assert np.array_equal(tag, want_tag), np.nonzero((tag != want_tag).any(axis=1))[0][:5]
+    for i in rng.choice(n, 60, replace=False):  # keystream per item (the oracle squeezes one length per call)
+        m = msgs[i]
+        if not m:
+            continue
+        ks = oracle.kmac_xof_batch(ke_ka[i, :64], np.array([0, 64], np.uint64), none, np.zeros(2, np.uint64), 8 * len(m), b"SKE", d,
+                                   threads=1)[0]
+        assert np.array_equal(ct[int(mo[i]):int(mo[i + 1])], ks ^ np.frombuffer(m, np.uint8)), (d, i, len(m))
+    out, ok = engine.sponge_decrypt(pd, po, b"".join(nonces), 512, ct, mo, tag, d)
+    assert ok.all() and np.array_equal(out, md)
