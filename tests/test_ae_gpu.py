@@ -237,3 +237,35 @@ def test_key_decrypt_handling_bad_input(gpu):
     assert all(r is not None and r.kind == "KeyDecryptionError" for r in res)
     assert [bytes(m.msg) for m in msgs] == enc
     assert gpu.key_decrypt([Message.new(b"x")], [b""])[0].kind == "SymNonceNotSet"
+
+
+@pytest.mark.parametrize("d", [224, 384])
+def test_key_encrypt_large_batch_against_c_oracle(engine, oracle, d):
+    """ECDHIES for a few hundred items (the two security parameters the small test above leaves out), expected values
+    composed from the C oracle: W.x from its ECDH, (ke || ka) = KMACXOF(W.x, "", 896, "PK"), t = KMACXOF(ka, m, 448, "PKA"),
+    c = KMACXOF(ke, "", |m|, "PKE") xor m  (ecc/encryptable.rs:36-45)."""
+    rng = np.random.default_rng(300 + d)
+    n = 200
+    msgs = [bytes(rng.integers(0, 256, size=int(k), dtype=np.uint8)) for k in rng.integers(0, 600, size=n)]
+    pws = [bytes(rng.integers(0, 256, size=int(k), dtype=np.uint8)) for k in rng.integers(0, 40, size=n)]
+    pd, po = pack(pws)
+    md, mo = pack(msgs)
+    pub = oracle.keygen_batch(pd, po, d, threads=0)
+    k_rand = rng.integers(0, 256, size=n * 56, dtype=np.uint8)
+    rc, ct, tag, z = engine.ed448_key_encrypt(pub, k_rand, md, mo, d)
+    assert rc == 0
+    rc2, wx = oracle.ecdh_batch(k_rand, pub, threads=0)
+    assert rc2 == 0
+    none, empty = np.zeros(0, np.uint8), np.zeros(n + 1, np.uint64)
+    ke_ka = oracle.kmac_xof_batch(wx.reshape(-1), np.arange(n + 1, dtype=np.uint64) * 56, none, empty, 896, b"PK", d, threads=0)
+    ka, kao = pack([r[56:].tobytes() for r in ke_ka])
+    assert np.array_equal(tag, oracle.kmac_xof_batch(ka, kao, md, mo, 448, b"PKA", d, threads=0))
+    for i in rng.choice(n, 40, replace=False):
+        if not msgs[i]:
+            continue
+        ks = oracle.kmac_xof_batch(ke_ka[i, :56], np.array([0, 56], np.uint64), none, np.zeros(2, np.uint64), 8 * len(msgs[i]), b"PKE",
+                                   d, threads=1)[0]
+        assert np.array_equal(ct[int(mo[i]):int(mo[i + 1])], ks ^ np.frombuffer(msgs[i], np.uint8)), (d, i)
+    # Z = [4 k mod r] G : decrypting with the right passwords must open everything
+    rc, out, ok = engine.ed448_key_decrypt(pd, po, z, ct, mo, tag, d)
+    assert rc == 0 and ok.all() and np.array_equal(out, md)
