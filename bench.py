@@ -35,6 +35,22 @@ MAC_VAR = 7.12e5
 PEAK_FALLBACK = {"lop3": 18.52e12, "imad_wide": 8.67e12}  # profiles/r01_peaks_int_pipes.json
 
 
+def host_threads() -> int:
+    """Host threads this process may use (the same call at every N: torchrun forces OMP_NUM_THREADS=1, which must
+    not decide how many cores the CPU reference gets)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def workload_config() -> dict:
+    """`config` of the JSON line -- the SAME dict in both arms (b200 and reference)."""
+    return {"workload": "sha3_256_2^20x64B", "per_gpu_msgs": N_MSGS, "msg_bytes": MSG_LEN, "sec_param": "D256",
+            "l2": f"inputs/outputs rotate over {N_ROT} buffer pairs (384 MiB per GPU > 126 MB L2)",
+            "sharding": "one 2^20-message batch per rank, no collective"}
+
+
 def _env_int(name, default):
     try:
         return int(os.environ.get(name, default))
@@ -102,62 +118,94 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------------
 # CPU baseline (oracle port) -- the ONLY place bench.py touches oracle/
 # ------------------------------------------------------------------------------------------------------
+def _time_sha3(orc, n, threads, lean, budget_s, rate_hint=None):
+    """GB/s of oracle.sha3_batch over n x 64 B messages, repeated for about budget_s."""
+    import numpy as np
+
+    rng = np.random.default_rng(1)
+    buf = rng.integers(0, 256, size=n * MSG_LEN, dtype=np.uint8)
+    off = np.arange(n + 1, dtype=np.uint64) * MSG_LEN
+    orc.sha3_batch(buf, off, 256, threads=threads, lean=lean)  # warm
+    t0 = time.perf_counter()
+    orc.sha3_batch(buf, off, 256, threads=threads, lean=lean)
+    rate = n / (time.perf_counter() - t0)
+    reps = max(1, int(rate * budget_s / n))
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        orc.sha3_batch(buf, off, 256, threads=threads, lean=lean)
+    dt = time.perf_counter() - t0
+    return n * reps * MSG_LEN / dt / 1e9, n * reps
+
+
 def cpu_sha3_baseline(budget_s: float, threads: int = 0):
-    """Times the structure-faithful C restatement (oracle/ref_cpu.c, -march=native) of
-    Message::compute_sha3_hash looped over 64-byte messages on `threads` host threads (0 = all)."""
+    """The CPU baselines BASELINE.md 2 names, on this box's host cores, SHA3-256 over 64-byte messages:
+      value / B-ref-parallel  the C restatement of Message::compute_sha3_hash (oracle/ref_cpu.c: message copy + pad +
+                              the wasted post-squeeze permutation, like the Rust code) under an OpenMP loop over
+                              messages (= a rayon par_iter wrapper), all host threads
+      serial_1core            the same code looped one message at a time on ONE core -- what the reference does today
+                              (src/sha3/hashable.rs:19-21 has no rayon)
+      lean_1core / lean_parallel  the restatement without the copy and the wasted permutation
+      openssl_1core           hashlib.sha3_256 (OpenSSL), one core, Python call overhead included
+    """
+    import hashlib
+
     import numpy as np
 
     from oracle import cpu
 
     orc = cpu.get(native=True)
-    cores = orc.max_threads if threads <= 0 else threads
+    cores = host_threads() if threads <= 0 else threads
+    par, n_par = _time_sha3(orc, 1 << 18, cores, 0, budget_s)
+    ser, n_ser = _time_sha3(orc, 1 << 15, 1, 0, budget_s / 2)
+    lean1, _ = _time_sha3(orc, 1 << 15, 1, 1, budget_s / 2)
+    leanp, _ = _time_sha3(orc, 1 << 18, cores, 1, budget_s / 2)
     rng = np.random.default_rng(1)
-    n_cal = 1 << 16
-    buf = rng.integers(0, 256, size=n_cal * MSG_LEN, dtype=np.uint8)
-    off = np.arange(n_cal + 1, dtype=np.uint64) * MSG_LEN
-    orc.sha3_batch(buf, off, 256, threads=threads)  # warm
+    msgs = [rng.integers(0, 256, size=MSG_LEN, dtype=np.uint8).tobytes() for _ in range(1 << 15)]
     t0 = time.perf_counter()
-    orc.sha3_batch(buf, off, 256, threads=threads)
-    rate = n_cal / (time.perf_counter() - t0)
-    n = int(min(N_MSGS, max(n_cal, rate * budget_s)))
-    buf = rng.integers(0, 256, size=n * MSG_LEN, dtype=np.uint8)
-    off = np.arange(n + 1, dtype=np.uint64) * MSG_LEN
-    reps = max(1, int(rate * budget_s / n))
-    t0 = time.perf_counter()
-    for _ in range(reps):
-        orc.sha3_batch(buf, off, 256, threads=threads)
-    dt = time.perf_counter() - t0
-    gbps = n * reps * MSG_LEN / dt / 1e9
+    for m in msgs:
+        hashlib.sha3_256(m).digest()
+    ossl = len(msgs) * MSG_LEN / (time.perf_counter() - t0) / 1e9
     return {
-        "value": gbps,
+        "value": par,
         "unit": "GB/s",
         "cores": cores,
         "kind": "port",
-        "sample": f"{reps} x {n} messages x {MSG_LEN} B, SHA3-256, oracle/ref_cpu.c (C restatement of the reference's "
-                  f"Rust path incl. its message copy and extra permutation), gcc -O3 -march=native, {cores} threads",
-        "msgs_per_s": n * reps / dt,
+        "sample": f"{n_par} messages x {MSG_LEN} B, SHA3-256, oracle/ref_cpu.c (C restatement of the reference's "
+                  f"Rust path incl. its message copy and extra permutation), gcc -O3 -march=native, {cores} threads "
+                  f"(B-ref-parallel of BASELINE.md 2)",
+        "msgs_per_s": par * 1e9 / MSG_LEN,
+        "legs": {
+            "serial_1core": {"value": ser, "unit": "GB/s", "cores": 1, "sample": f"{n_ser} messages, same code, one core: "
+                             "what Message::compute_sha3_hash looped does today (no rayon on this path)"},
+            "lean_1core": {"value": lean1, "unit": "GB/s", "cores": 1,
+                           "sample": "restatement without the message copy and the wasted post-squeeze permutation"},
+            "lean_parallel": {"value": leanp, "unit": "GB/s", "cores": cores, "sample": "lean variant, all host threads"},
+            "openssl_1core": {"value": ossl, "unit": "GB/s", "cores": 1,
+                              "sample": f"hashlib.sha3_256 over {len(msgs)} x {MSG_LEN} B (OpenSSL; Python call overhead included)"},
+        },
     }
 
 
 def cpu_ed448_baseline(budget_s: float, threads: int = 0):
     """The Ed448 half of the metric on the host: KeyPair::new-style [s]G (the reference multiplies the generator with
     its generic variable-base routine, ecc/keypair.rs:44), sign and verify, through the C restatement on `threads`
-    host threads (0 = all).  Bounded samples sized from a calibration run."""
+    host threads (0 = all) and on one core (what the reference does today), plus OpenSSL Ed448 (`cryptography`) on one
+    core as an outside yardstick (a different signature protocol).  Bounded samples sized from a calibration run."""
     import numpy as np
 
     from oracle import cpu
 
     orc = cpu.get(native=True)
-    cores = orc.max_threads if threads <= 0 else threads
+    cores = host_threads() if threads <= 0 else threads
     rng = np.random.default_rng(3)
 
-    def rate(fn, n_cal, make):
+    def rate(fn, n_cal, make, budget):
         args = make(n_cal)
         fn(*args)
         t0 = time.perf_counter()
         fn(*args)
         r = n_cal / (time.perf_counter() - t0)
-        n = int(max(n_cal, min(1 << 16, r * budget_s)))
+        n = int(max(n_cal, min(1 << 16, r * budget)))
         args = make(n)
         t0 = time.perf_counter()
         fn(*args)
@@ -171,23 +219,52 @@ def cpu_ed448_baseline(budget_s: float, threads: int = 0):
         msg = rng.integers(0, 256, size=n * 256, dtype=np.uint8)
         return pw, np.arange(n + 1, dtype=np.uint64) * 32, msg, np.arange(n + 1, dtype=np.uint64) * 256
 
-    fb, n_fb = rate(lambda sc: orc.fixed_base_batch(sc, threads=threads), 256, mk_sc)
-    sg, n_sg = rate(lambda pw, po, m, mo: orc.sign_batch(pw, po, m, mo, 512, threads=threads), 256, mk_sign)
-    pw, po, m, mo = mk_sign(min(n_sg, 2048))
-    pub = orc.keygen_batch(pw, po, 512, threads=threads)
-    h, z = orc.sign_batch(pw, po, m, mo, 512, threads=threads)
-    t0 = time.perf_counter()
-    orc.verify_batch(pub, m, mo, h, z, 512, threads=threads)
-    vf = (len(po) - 1) / (time.perf_counter() - t0)
-    return {"scalar_mults_per_s": fb, "signs_per_s": sg, "verifies_per_s": vf, "unit": "1/s", "cores": cores, "kind": "port",
-            "sample": f"{n_fb} generator multiplications, {n_sg} signatures, {len(po) - 1} verifications (32-byte passwords, "
-                      f"256-byte messages, D512), oracle/ref_cpu.c (64-bit limbs, u128 products, signed radix-16 window like "
-                      f"the crate), gcc -O3 -march=native, {cores} threads"}
+    def measure(t, budget):
+        fb, n_fb = rate(lambda sc: orc.fixed_base_batch(sc, threads=t), 64 * t, mk_sc, budget)
+        sg, n_sg = rate(lambda pw, po, m, mo: orc.sign_batch(pw, po, m, mo, 512, threads=t), 64 * t, mk_sign, budget)
+        pw, po, m, mo = mk_sign(min(n_sg, 2048))
+        pub = orc.keygen_batch(pw, po, 512, threads=t)
+        h, z = orc.sign_batch(pw, po, m, mo, 512, threads=t)
+        t0 = time.perf_counter()
+        orc.verify_batch(pub, m, mo, h, z, 512, threads=t)
+        vf = (len(po) - 1) / (time.perf_counter() - t0)
+        return {"scalar_mults_per_s": fb, "signs_per_s": sg, "verifies_per_s": vf, "cores": t,
+                "sample": f"{n_fb} generator multiplications, {n_sg} signatures, {len(po) - 1} verifications"}
+
+    par = measure(cores, budget_s)
+    out = {**par, "unit": "1/s", "kind": "port",
+           "sample": par["sample"] + f" (32-byte passwords, 256-byte messages, D512), oracle/ref_cpu.c (64-bit limbs, u128 "
+                                     f"products, signed radix-16 window like the crate), gcc -O3 -march=native, {cores} threads",
+           "legs": {"serial_1core": measure(1, budget_s / 2)}}
+    try:  # B-openssl: outside yardstick, one core
+        from cryptography.hazmat.primitives.asymmetric.ed448 import Ed448PrivateKey
+
+        n = 200
+        msg = bytes(256)
+        t0 = time.perf_counter()
+        keys = [Ed448PrivateKey.generate() for _ in range(n)]
+        pubs = [k.public_key() for k in keys]
+        t_k = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        sigs = [k.sign(msg) for k in keys]
+        t_s = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        for p_, s_ in zip(pubs, sigs):
+            p_.verify(s_, msg)
+        t_v = time.perf_counter() - t0
+        out["legs"]["openssl_1core"] = {"scalar_mults_per_s": n / t_k, "signs_per_s": n / t_s, "verifies_per_s": n / t_v,
+                                        "cores": 1, "sample": f"{n} x OpenSSL Ed448 (RFC 8032 EdDSA, not the reference's "
+                                                              "Schnorr variant) keygen / sign 256 B / verify via `cryptography`"}
+    except Exception as e:  # pragma: no cover
+        out["legs"]["openssl_1core"] = {"unavailable": repr(e)}
+    return out
 
 
 def run_reference(args, rank: int):
     """--impl reference: the reference's own CPU implementation of the path on the host cores.  The Rust
-    reference cannot be built in this image (no rustc/cargo), so this is the oracle port."""
+    reference cannot be built in this image (no rustc/cargo), so this is the oracle port.  The same program at every
+    N: rank 0 alone runs it, on every host thread the process may use (explicit thread count -- torchrun's
+    OMP_NUM_THREADS=1 does not apply)."""
     if rank != 0:
         return
     import numpy as np
@@ -195,24 +272,24 @@ def run_reference(args, rank: int):
     from oracle import cpu
 
     orc = cpu.get(native=True)
-    cores = orc.max_threads
+    cores = host_threads()
     rng = np.random.default_rng(1)
     n_cal = 1 << 16
     buf = rng.integers(0, 256, size=n_cal * MSG_LEN, dtype=np.uint8)
     off = np.arange(n_cal + 1, dtype=np.uint64) * MSG_LEN
-    orc.sha3_batch(buf, off, 256, threads=0)
+    orc.sha3_batch(buf, off, 256, threads=cores)
     t0 = time.perf_counter()
-    orc.sha3_batch(buf, off, 256, threads=0)
+    orc.sha3_batch(buf, off, 256, threads=cores)
     rate = n_cal / (time.perf_counter() - t0)
     total_budget_s = 90.0
     n = int(min(N_MSGS, max(4096, rate * total_budget_s / max(1, args.steps + args.warmup))))
     buf = rng.integers(0, 256, size=n * MSG_LEN, dtype=np.uint8)
     off = np.arange(n + 1, dtype=np.uint64) * MSG_LEN
     for _ in range(args.warmup):
-        orc.sha3_batch(buf, off, 256, threads=0)
+        orc.sha3_batch(buf, off, 256, threads=cores)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        orc.sha3_batch(buf, off, 256, threads=0)
+        orc.sha3_batch(buf, off, 256, threads=cores)
     dt = time.perf_counter() - t0
     gbps = n * args.steps * MSG_LEN / dt / 1e9
     sample = (f"each step = {n} of the {N_MSGS} messages x {MSG_LEN} B (bounded sample), oracle/ref_cpu.c restatement of "
@@ -221,11 +298,11 @@ def run_reference(args, rank: int):
         "impl": "reference", "metric": "sha3_256_GBps", "value": gbps, "unit": "GB/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": "sha3_256_2^20x64B", "msgs_per_step": n, "msg_bytes": MSG_LEN},
+        "config": workload_config(), "sample_msgs_per_step": n,
         "cpu_baseline": {"value": gbps, "unit": "GB/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": gbps, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-        "extra": {"ed448_cpu": cpu_ed448_baseline(budget_s=1.0)},
+        "extra": {"ed448_cpu": cpu_ed448_baseline(budget_s=1.0, threads=cores)},
     }
     emit_json_line(line)
 
@@ -416,9 +493,7 @@ def main():
         "metric": "sha3_256_GBps", "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": "sha3_256_2^20x64B", "per_gpu_msgs": N_MSGS, "msg_bytes": MSG_LEN, "sec_param": "D256",
-                   "l2": f"inputs/outputs rotate over {N_ROT} buffer pairs (384 MiB per GPU > 126 MB L2)",
-                   "sharding": "one 2^20-message batch per rank, no collective"},
+        "config": workload_config(),
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
         "msgs_per_s": world * N_MSGS / (ms_per_step * 1e-3),
     }

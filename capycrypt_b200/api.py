@@ -145,6 +145,10 @@ class Gpu:
                 res[i] = OperationError("SignatureNotSet")
             elif m.d is None:
                 res[i] = OperationError("SecurityParameterNotSet")
+            elif len(m.sig.h) != 56 or len(m.sig.z) != 56 or len(pub_keys[i]) != 112:
+                # a malformed signature or key fails on its own and is left out of the fixed-stride batch (one short
+                # field would otherwise shift every later item); the reference rejects it at the type level
+                res[i] = OperationError("SignatureVerificationFailure")
             else:
                 groups.setdefault(int(m.d), []).append(i)
         for d, idx in groups.items():
@@ -168,6 +172,8 @@ class Gpu:
         d = SecParam.try_from(int(d))
         if nonces is None:
             nonces = [os.urandom(512) for _ in msgs]
+        if len(nonces) != len(msgs) or len(pws) != len(msgs) or any(len(z) != 512 for z in nonces):
+            raise ValueError("sha3_encrypt: one password and one 512-byte nonce per message")
         pd, po = pack(pws)
         md, mo = pack([m.msg for m in msgs])
         ct, tag = self.engine.sponge_encrypt(pd, po, b"".join(nonces), 512, md, mo, int(d))
@@ -210,6 +216,12 @@ class Gpu:
         d = SecParam.try_from(int(d))
         if k_rand is None:
             k_rand = [os.urandom(56) for _ in msgs]
+        if len(pub_keys) != len(msgs) or len(k_rand) != len(msgs):
+            raise ValueError("key_encrypt: one public key and one nonce per message")
+        for i in range(len(msgs)):
+            if len(pub_keys[i]) != 112 or len(k_rand[i]) != 56:
+                # (an ExtendedPoint / a 56-byte get_random_bytes in the reference: cannot be malformed there)
+                raise ValueError(f"key_encrypt: item {i}: public key must be 112 bytes and the nonce 56 bytes")
         md, mo = pack([m.msg for m in msgs])
         rc, ct, tag, z = self.engine.ed448_key_encrypt(b"".join(pub_keys), b"".join(k_rand), md, mo, int(d))
         if rc:
@@ -230,6 +242,8 @@ class Gpu:
                 res[i] = OperationError("SymNonceNotSet")
             elif m.d is None:
                 res[i] = OperationError("SecurityParameterNotSet")
+            elif len(m.asym_nonce) != 112:
+                res[i] = OperationError("KeyDecryptionError")  # not a point encoding: fails alone, stays out of the batch
             else:
                 groups.setdefault(int(m.d), []).append(i)
         for d, idx in groups.items():

@@ -18,16 +18,9 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "_lib")
 LIB = os.path.join(LIBDIR, "libcapycrypt_gpu.so")
 SOURCES = ["ctx.cu", "sha3_api.cu", "ed448_api.cu", "ed448_fixed.cu", "ed448_var.cu", "ae_api.cu"]
-# per-source tuning, from measurements on B200 (profiles/README.md).  Variable-base ladder: the four doublings of a
-# window are one rolled loop with the field multiplications INLINED (operands stay in registers), the addition that
-# closes the window calls out-of-line multiplications (keeps the loop body at ~8 multiplication bodies, which the
-# instruction prefetcher streams like the fixed-base comb), the warps of a block pass every doubling together (one
-# instruction stream per block), 168 registers = 3 blocks/SM.  Measured for 2^18 items: this build 31.0-31.5 ms;
-# everything out-of-line at 128 registers 32.6 ms; everything inlined 32.1 ms (3 blocks/SM) / 35.2 ms (1 x 256
-# threads); without the barrier the inlined loops lose 10-20 % to instruction-fetch stalls.  The fixed-base comb is
-# fastest fully inlined.
-PER_SOURCE_DEFINES = {"ed448_var.cu": ["-DCAPY_FE_OOL", "-DCAPY_VB_HOT_INLINE", "-DCAPY_VB_ADD_OOL", "-DCAPY_VB_SYNC",
-                                       "-DCAPY_ED_MINBLOCKS=3"]}
+# per-source defines (none at present: both curve kernels are fastest with every field multiplication inlined --
+# csrc/ed448_var.cu and csrc/ed448_fixed.cu explain their code shape)
+PER_SOURCE_DEFINES = {}
 NVCC = os.environ.get("NVCC", "nvcc")
 BASE_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -124,29 +124,6 @@ CAPY_HD bool pt_from_affine(PtExt& p, const Fe& x, const Fe& y) {
   return fe_is_zero(l);
 }
 
-// ---- signed radix-16 recoding -----------------------------------------------------------------
-// digits d_i in [-8, 7] (i < 112) with sum d_i 16^i = k; dig[112] is the final carry (0 or 1),
-// which is always 0 when k < 2^446 (reduced scalars).
-CAPY_HD void sc_recode_radix16(int8_t* dig /*[113]*/, const Sc& k) {
-  uint32_t carry = 0;
-#pragma unroll 1
-  for (int i = 0; i < 112; i++) {
-    uint32_t nib = ((k.w[i >> 3] >> (4 * (i & 7))) & 15u) + carry;
-    carry = nib >= 8u ? 1u : 0u;
-    dig[i] = (int8_t)((int32_t)nib - (int32_t)(carry << 4));
-  }
-  dig[112] = (int8_t)carry;
-}
-
-// constant-time conditional negation of a cached entry: -(X:Y:Z:T) = (-X:Y:Z:-T)
-CAPY_HD void ptcached_cneg(PtCached& e, uint32_t neg_mask) {
-  Fe nx, ntd;
-  fe_neg(nx, e.X);
-  fe_neg(ntd, e.Td);
-  fe_cmov(e.X, nx, neg_mask);
-  fe_cmov(e.Td, ntd, neg_mask);
-}
-
 // ---- fixed-base comb on the 4-isogenous twisted curve ------------------------------------------------
 // [k]G is computed as  phi^([k / 4 mod r] * phi(G))  where phi: E -> E' is the 4-isogeny onto the twisted
 // Edwards curve E': -x^2 + y^2 = 1 + (d - 1) x^2 y^2 and phi^ its dual (phi^ o phi = [4]; G has odd order r,
@@ -288,59 +265,252 @@ CAPY_HD void pt_fixed_base_mul(PtExt& r, const Sc& k, const uint32_t* __restrict
 }
 
 // ---- variable base ------------------------------------------------------------------------------
-// tab[j] = (j+1) * P, j = 0..7, as cached projective entries
-CAPY_HD void vb_build_table(PtCached* tab /*[8]*/, const PtExt& p) {
-  PtExt acc;
-  pt_to_cached(tab[0], p);
-  pt_double<true>(acc, p);
-  pt_to_cached(tab[1], acc);
-#pragma unroll 1
-  for (int j = 2; j < 8; j++) {
-    pt_add_cached<true>(acc, acc, tab[0]);
-    pt_to_cached(tab[j], acc);
+// [k]P for the exact integer k < 2^448 (NOT reduced: quirk Q10, ecc/signable.rs:76-77), signed radix-16 fixed
+// window, per-item table 1P..8P.  The table lives in memory the caller provides (the CUDA kernel: shared memory,
+// thread-interleaved).  An entry is a cached point (X, Y, Z, d*T) with every coordinate carried to its exact
+// 448-bit value and packed into 14 words: 56 words = 14 uint4 chunks; chunk c of entry e sits at
+// col[(e * 14 + c) * STRIDE], where col already points at this item's column.
+//
+// The whole computation is ONE loop whose body holds one copy of the doubling (4 S + 4 M) and one copy of the
+// addition (9 M), all multiplications inlined: table construction (2P = dbl, jP = (j-1)P + P), the 113 windows
+// (4 doublings + 1 addition of a looked-up entry) and the optional addend of verify (U = [z]G + [h]V,
+// ecc/signable.rs:77) are iterations of that loop with different operands, so the accumulator never leaves the
+// registers and no multiplication goes through an out-of-line call.
+// The signed digits are not stored: with K = k + 0x888...8 (112 nibbles) digit i is nibble i of K minus 8 (the
+// digits in [-8, 7] a carry recoding gives; the last one, digit 112, is 0 or 1); K sits in 15 registers and is shifted left by one nibble per
+// window, so the current digit is always at bit 448.
+constexpr int VB_ENTRIES = 8;
+constexpr int VB_CHUNKS = 14;  // uint4 chunks per entry: X | Y | Z | d*T, 14 words each
+
+#if defined(__CUDA_ARCH__)
+#define CAPY_BLOCK_SYNC() __syncthreads()
+CAPY_HD uint32_t capy_fshr(uint32_t lo, uint32_t hi, uint32_t sh) { return __funnelshift_r(lo, hi, sh); }
+CAPY_HD uint32_t capy_fshl(uint32_t lo, uint32_t hi, uint32_t sh) { return __funnelshift_l(lo, hi, sh); }
+#else
+#define CAPY_BLOCK_SYNC() ((void)0)
+CAPY_HD uint32_t capy_fshr(uint32_t lo, uint32_t hi, uint32_t sh) { return (uint32_t)((((uint64_t)hi << 32) | lo) >> sh); }
+CAPY_HD uint32_t capy_fshl(uint32_t lo, uint32_t hi, uint32_t sh) { return (uint32_t)(((((uint64_t)hi << 32) | lo) << sh) >> 32); }
+#endif
+
+// tight limbs -> the exact 448-bit value in limbs < 2^28 (not necessarily < p): two serial passes; the second
+// cannot carry out (value < 2^448 (1 + 2^-18): after a wrap the value is tiny)
+CAPY_HD void fe_carry_exact(Fe& a) {
+#pragma unroll
+  for (int pass = 0; pass < 2; pass++) {
+    uint32_t c = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+      const uint32_t v = a.v[i] + c;
+      a.v[i] = v & M28;
+      c = v >> 28;
+    }
+    a.v[0] += c;  // 2^448 = 2^224 + 1
+    a.v[8] += c;
   }
 }
 
-CAPY_HD void vb_lookup(PtCached& e, const PtCached* tab, int dgt, bool CONSTANT_TIME) {
+// limbs < 2^28 -> 14 little-endian words at w[0..13], and back
+CAPY_HD void fe_pack14(uint32_t* w, const Fe& a) {
+#pragma unroll
+  for (int q = 0; q < 14; q++) w[q] = 0;
+#pragma unroll
+  for (int i = 0; i < 16; i++) {
+    const int bit = 28 * i, q = bit >> 5, sh = bit & 31;
+    w[q] |= a.v[i] << sh;
+    if (sh > 4 && q + 1 < 14) w[q + 1] |= a.v[i] >> (32 - sh);
+  }
+}
+CAPY_HD void fe_unpack14(Fe& r, const uint32_t* w) {
+#pragma unroll
+  for (int i = 0; i < 16; i++) {
+    const int bit = 28 * i, q = bit >> 5, sh = bit & 31;
+    uint32_t v;
+    if (sh == 0) v = w[q];
+    else if (sh > 4 && q + 1 < 14) v = capy_fshr(w[q], w[q + 1], sh);
+    else v = w[q] >> sh;
+    r.v[i] = v & M28;
+  }
+}
+
+// entry e of this item := cached form of p (X, Y, Z, d*T)
+template <int STRIDE>
+CAPY_HD void vb_store_entry(uint4* col, int e, const PtExt& p) {
+  uint32_t w[56];
+  Fe t;
+  fe_copy(t, p.X);
+  fe_carry_exact(t);
+  fe_pack14(w, t);
+  fe_copy(t, p.Y);
+  fe_carry_exact(t);
+  fe_pack14(w + 14, t);
+  fe_copy(t, p.Z);
+  fe_carry_exact(t);
+  fe_pack14(w + 28, t);
+  fe_mul_d(t, p.T);
+  fe_carry_exact(t);
+  fe_pack14(w + 42, t);
+  uint4* ent = col + (size_t)e * VB_CHUNKS * STRIDE;
+#pragma unroll
+  for (int c = 0; c < VB_CHUNKS; c++) {
+    uint4 v;
+    v.x = w[4 * c];
+    v.y = w[4 * c + 1];
+    v.z = w[4 * c + 2];
+    v.w = w[4 * c + 3];
+    ent[c * STRIDE] = v;
+  }
+}
+
+// e = dgt * P from the table (dgt in [-8, 8]); constant time = every entry is read and the wanted one kept with a
+// mask.  The negation -(X : Y : Z : T) = (-X : Y : Z : -T) is left unreduced (2p - v, alpha 2): the addition
+// multiplies it with tight operands only.
+template <int STRIDE>
+CAPY_HD void vb_lookup(PtCached& e, const uint4* col, int dgt, bool CONSTANT_TIME) {
   const uint32_t neg = dgt < 0 ? 0xffffffffu : 0u;
   const uint32_t mag = (uint32_t)(dgt < 0 ? -dgt : dgt);
-  // identity as a cached entry: X = 0, Y = 1, Z = 1, Td = 0
-  fe_zero(e.X);
-  fe_one(e.Y);
-  fe_one(e.Z);
-  fe_zero(e.Td);
+  uint32_t w[56];
   if (CONSTANT_TIME) {
+#pragma unroll
+    for (int k = 0; k < 56; k++) w[k] = 0;
 #pragma unroll 1
-    for (uint32_t j = 1; j <= 8; j++) {
+    for (uint32_t j = 1; j <= (uint32_t)VB_ENTRIES; j++) {
       const uint32_t m = (j == mag) ? 0xffffffffu : 0u;
-      fe_cmov(e.X, tab[j - 1].X, m);
-      fe_cmov(e.Y, tab[j - 1].Y, m);
-      fe_cmov(e.Z, tab[j - 1].Z, m);
-      fe_cmov(e.Td, tab[j - 1].Td, m);
+      const uint4* ent = col + (size_t)(j - 1) * VB_CHUNKS * STRIDE;
+#pragma unroll
+      for (int c = 0; c < VB_CHUNKS; c++) {
+        const uint4 v = ent[c * STRIDE];
+        w[4 * c + 0] |= v.x & m;
+        w[4 * c + 1] |= v.y & m;
+        w[4 * c + 2] |= v.z & m;
+        w[4 * c + 3] |= v.w & m;
+      }
     }
-  } else if (mag != 0) {
-    e = tab[mag - 1];
+  } else {
+    const uint4* ent = col + (size_t)(mag ? mag - 1 : 0) * VB_CHUNKS * STRIDE;
+    const uint32_t m = mag ? 0xffffffffu : 0u;
+#pragma unroll
+    for (int c = 0; c < VB_CHUNKS; c++) {
+      const uint4 v = ent[c * STRIDE];
+      w[4 * c + 0] = v.x & m;
+      w[4 * c + 1] = v.y & m;
+      w[4 * c + 2] = v.z & m;
+      w[4 * c + 3] = v.w & m;
+    }
   }
-  ptcached_cneg(e, neg);
+  const uint32_t one = mag ? 0u : 1u;  // digit 0: the identity (0 : 1 : 1 : 0)
+  w[14] |= one;
+  w[28] |= one;
+  Fe x, td;
+  fe_unpack14(x, w);
+  fe_unpack14(e.Y, w + 14);
+  fe_unpack14(e.Z, w + 28);
+  fe_unpack14(td, w + 42);
+#pragma unroll
+  for (int i = 0; i < 16; i++) {
+    const uint32_t twop = i == 8 ? 2u * (M28 - 1u) : 2u * M28;
+    e.X.v[i] = ((twop - x.v[i]) & neg) | (x.v[i] & ~neg);
+    e.Td.v[i] = ((twop - td.v[i]) & neg) | (td.v[i] & ~neg);
+  }
 }
 
-// r = [k]P for the exact integer k < 2^448 (NOT reduced: quirk Q10, ecc/signable.rs:76-77)
-CAPY_HD void pt_var_base_mul(PtExt& r, const Sc& k, const PtExt& p, PtCached* tab /*[8] scratch*/, int8_t* dig /*[113]*/,
-                             bool CONSTANT_TIME) {
-  vb_build_table(tab, p);
-  sc_recode_radix16(dig, k);
-  pt_identity(r);
-#pragma unroll 1
-  for (int i = 112; i >= 0; i--) {
-    if (i != 112) {
-      pt_double<false>(r, r);
-      pt_double<false>(r, r);
-      pt_double<false>(r, r);
-      pt_double<true>(r, r);
+// r = 2r (dbl-2008-hwcd, a = 1): 4 S + 3 M (+ 1 M for T), multiplications inlined
+CAPY_HD void vb_double(PtExt& r, bool want_t) {
+  Fe A, B, C, E, F, G, H, s, ZZ;
+  fe_sqr_inl(A, r.X);
+  fe_sqr_inl(B, r.Y);
+  fe_sqr_inl(ZZ, r.Z);
+  fe_add(s, r.X, r.Y);   // alpha 2
+  fe_sqr_inl(E, s);      // 2 x 2
+  fe_add(G, A, B);       // alpha 2
+  fe_sub4(E, E, G);      // alpha 5
+  fe_weak(E);            // tight
+  fe_add(C, ZZ, ZZ);     // alpha 2
+  fe_sub4(F, G, C);      // alpha 6
+  fe_weak(F);            // tight
+  fe_sub(H, A, B);       // alpha 3
+  fe_mul_inl(r.X, E, F);
+  fe_mul_inl(r.Y, G, H);
+  fe_mul_inl(r.Z, F, G);
+  if (want_t) fe_mul_inl(r.T, E, H);
+}
+
+// r = r + q (add-2008-hwcd, a = 1, q cached with alpha(q.X), alpha(q.Td) <= 2): 9 M.  Ordered so that few field
+// elements are live at a time (the operands of r and q die early): the inlined body fits the registers.
+CAPY_HD void vb_add(PtExt& r, const PtCached& q) {
+  Fe A, B, E, H, s1, s2;
+  fe_add(s1, r.X, r.Y);       // alpha 2
+  fe_add(s2, q.X, q.Y);       // alpha 3
+  fe_mul_inl(E, s1, s2);      // 2 x 3: (X1 + Y1)(X2 + Y2)
+  fe_mul_inl(A, r.X, q.X);    // 1 x 2
+  fe_mul_inl(B, r.Y, q.Y);
+  fe_add(s1, A, B);           // alpha 2
+  fe_sub4(E, E, s1);          // alpha 5
+  fe_weak(E);                 // tight
+  fe_sub(H, B, A);            // alpha 3
+  Fe C, D, F, G;
+  fe_mul_inl(C, r.T, q.Td);   // 1 x 2
+  fe_mul_inl(D, r.Z, q.Z);
+  fe_sub(F, D, C);            // alpha 3
+  fe_add(G, D, C);            // alpha 2
+  fe_mul_inl(r.X, E, F);
+  fe_mul_inl(r.Y, G, H);
+  fe_mul_inl(r.Z, F, G);
+  fe_mul_inl(r.T, E, H);
+}
+
+// r = [k]P (+ addend).  On entry r = P (extended, tight); `load_addend(PtExt&)` is only called when has_addend.
+// In a CUDA block every thread must call this (block barriers keep the warps on one instruction stream).
+template <int STRIDE, class LoadAddend>
+CAPY_HD void pt_var_base_mul(PtExt& r, const Sc& k, uint4* col, bool CONSTANT_TIME, bool has_addend, LoadAddend&& load_addend) {
+  uint32_t K[15];
+  {
+    uint64_t c = 0;
+#pragma unroll
+    for (int j = 0; j < 14; j++) {
+      const uint64_t t = (uint64_t)k.w[j] + 0x88888888u + c;
+      K[j] = (uint32_t)t;
+      c = t >> 32;
     }
-    PtCached e;
-    vb_lookup(e, tab, (int)dig[i], CONSTANT_TIME);
-    pt_add_cached<true>(r, r, e);
+    K[14] = (uint32_t)c;
+  }
+  vb_store_entry<STRIDE>(col, 0, r);  // 1P
+  // iterations 0..6 build 2P..8P, 7..119 are the windows 112..0, 120 adds the addend
+  const int n_it = has_addend ? 121 : 120;
+#pragma unroll 1
+  for (int it = 0; it < n_it; it++) {
+    int n_dbl = 0, dgt = 1, store_idx = -1;
+    bool do_add = true, ct = false;
+    if (it == 0) {
+      n_dbl = 1;
+      do_add = false;
+      store_idx = 1;
+    } else if (it < 7) {
+      store_idx = it + 1;
+    } else if (it < 120) {
+      if (it == 7) pt_identity(r);
+      else n_dbl = 4;
+      dgt = (int)(K[14] & 15u) - (it == 7 ? 0 : 8);
+#pragma unroll
+      for (int j = 14; j > 0; j--) K[j] = capy_fshl(K[j - 1], K[j], 4);
+      K[0] <<= 4;
+      ct = CONSTANT_TIME;
+    } else {
+      PtExt a;  // the table is dead: entry 0 := addend
+      load_addend(a);
+      vb_store_entry<STRIDE>(col, 0, a);
+    }
+#pragma unroll 1
+    for (int d = 0; d < n_dbl; d++) {
+      CAPY_BLOCK_SYNC();  // one instruction stream per block
+      vb_double(r, d == n_dbl - 1);
+    }
+    if (do_add) {
+      PtCached e;
+      vb_lookup<STRIDE>(e, col, dgt, ct);
+      CAPY_BLOCK_SYNC();
+      vb_add(r, e);
+    }
+    if (store_idx >= 0) vb_store_entry<STRIDE>(col, store_idx, r);
   }
 }
 

@@ -25,11 +25,12 @@
 constexpr int ILP = 8;
 constexpr int INNER = 16;  // unrolled repetitions of the ILP group per loop iteration
 
-enum Kind { LOP3, SHF, IADD3, IMAD, IMADWIDE, IMADHI, MIX_LOP3_IMAD, MIX_LOP3_SHF, MIX_LOP3_IMADWIDE, MIX_KECCAK_FMA, DFMA, FFMA, NKINDS };
+enum Kind { LOP3, SHF, IADD3, IMAD, IMADWIDE, IMADHI, MIX_LOP3_IMAD, MIX_LOP3_SHF, MIX_LOP3_IMADWIDE, MIX_KECCAK_FMA, DFMA, FFMA, MIX_DFMA_LOP3, MIX_DFMA_IMADWIDE, MIX_DFMA_IADD64, MIX_DFMA_DADD_IADD64, NKINDS };
 static const char* kNames[NKINDS] = {"lop3", "shf", "iadd3", "imad", "imad_wide", "imad_hi", "mix_lop3_imad",
-                                     "mix_lop3_shf", "mix_lop3_imadwide", "mix_2lop3_1imadwide", "dfma", "ffma"};
+                                     "mix_lop3_shf", "mix_lop3_imadwide", "mix_2lop3_1imadwide", "dfma", "ffma", "mix_dfma_lop3",
+                                     "mix_dfma_imadwide", "mix_dfma_iadd64", "mix_2dfma_dadd_2iadd64"};
 // thread-ops per ILP-group element (mixes issue two instructions per element)
-static const int kOpsPerElem[NKINDS] = {1, 1, 1, 1, 1, 1, 2, 2, 2, 3, 1, 1};
+static const int kOpsPerElem[NKINDS] = {1, 1, 1, 1, 1, 1, 2, 2, 2, 3, 1, 1, 2, 2, 2, 5};
 
 template <int KIND>
 __global__ void __launch_bounds__(256) peak_kernel(uint32_t* out, long long* cycles, int iters, uint32_t seed) {
@@ -50,7 +51,7 @@ __global__ void __launch_bounds__(256) peak_kernel(uint32_t* out, long long* cyc
   for (int r = 0; r < INNER; r++) bv[r] = seed * (2 * r + 3) + threadIdx.x;
   long long t0 = clock64();
   for (int it = 0; it < iters; it++) {
-    if (KIND == IMADWIDE || KIND == MIX_LOP3_IMADWIDE || KIND == MIX_KECCAK_FMA) {
+    if (KIND == IMADWIDE || KIND == MIX_LOP3_IMADWIDE || KIND == MIX_KECCAK_FMA || KIND == MIX_DFMA_IMADWIDE) {
 #pragma unroll
       for (int i = 0; i < ILP; i++) a2[i] ^= (uint32_t)(w[i] >> 7);  // keeps the products loop-variant
     }
@@ -83,6 +84,28 @@ __global__ void __launch_bounds__(256) peak_kernel(uint32_t* out, long long* cyc
         }
         if (KIND == DFMA) asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(dd[i]) : "d"(1.0000001), "d"(0.5));
         if (KIND == FFMA) asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(ff[i]) : "f"(1.0000001f), "f"(0.5f));
+        // FP64 pipe against the integer pipes: is DFMA (64 lanes/clk/SM on B200) a third pipe that overlaps LOP3 /
+        // IMAD.WIDE / 64-bit adds?  (the question behind a double-precision-FMA field multiplier)
+        if (KIND == MIX_DFMA_LOP3) {
+          asm volatile("fma.rz.f64 %0, %0, %1, %2;" : "+d"(dd[i]) : "d"(1.0000001), "d"(0.5));
+          asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[i]) : "r"(b), "r"(c));
+        }
+        if (KIND == MIX_DFMA_IMADWIDE) {
+          asm volatile("fma.rz.f64 %0, %0, %1, %2;" : "+d"(dd[i]) : "d"(1.0000001), "d"(0.5));
+          w[i] += (uint64_t)a2[i] * bv[r];
+        }
+        if (KIND == MIX_DFMA_IADD64) {
+          asm volatile("fma.rz.f64 %0, %0, %1, %2;" : "+d"(dd[i]) : "d"(1.0000001), "d"(0.5));
+          asm volatile("add.u64 %0, %0, %1;" : "+l"(w[i]) : "l"((uint64_t)bv[r] << 20));
+        }
+        if (KIND == MIX_DFMA_DADD_IADD64) {  // the per-product work of the split-product scheme: 2 DFMA + 1 DADD + 2 x 64-bit add
+          double hi, lo;
+          asm volatile("fma.rz.f64 %0, %1, %2, %3;" : "=d"(hi) : "d"(dd[i]), "d"(1.0000001), "d"(4503599627370496.0));
+          asm volatile("sub.rz.f64 %0, %1, %2;" : "=d"(lo) : "d"(4503599627370497.0), "d"(hi));
+          asm volatile("fma.rz.f64 %0, %1, %2, %0;" : "+d"(lo) : "d"(dd[i]), "d"(1.0000001));
+          w[i] += (uint64_t)__double_as_longlong(hi);
+          w[(i + 1) % ILP] += (uint64_t)__double_as_longlong(lo);
+        }
       }
     }
   }
@@ -158,6 +181,10 @@ int main(int argc, char** argv) {
   run<MIX_KECCAK_FMA>(sms, iters, d_out, d_cyc, json);
   run<DFMA>(sms, iters, d_out, d_cyc, json);
   run<FFMA>(sms, iters, d_out, d_cyc, json);
+  run<MIX_DFMA_LOP3>(sms, iters, d_out, d_cyc, json);
+  run<MIX_DFMA_IMADWIDE>(sms, iters, d_out, d_cyc, json);
+  run<MIX_DFMA_IADD64>(sms, iters, d_out, d_cyc, json);
+  run<MIX_DFMA_DADD_IADD64>(sms, iters, d_out, d_cyc, json);
   int clk_khz = 0;
   cudaDeviceGetAttribute(&clk_khz, cudaDevAttrClockRate, 0);
   char tail[256];

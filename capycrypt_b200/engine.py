@@ -35,6 +35,23 @@ def _hp(a: np.ndarray | None):
 _DUMMY = np.zeros(16, np.uint8)
 
 
+def _need(buf: np.ndarray, nbytes: int, what: str) -> None:
+    """The C side trusts (pointer, n): refuse a buffer shorter than n * stride here instead of letting the
+    library read past a numpy allocation."""
+    if buf.size < nbytes:
+        raise ValueError(f"{what}: {buf.size} bytes, need {nbytes}")
+
+
+def _need_packed(data: np.ndarray, off: np.ndarray, what: str) -> int:
+    """packed batch = bytes + offsets[n + 1]: offsets start inside the buffer, never decrease, end inside it."""
+    if off.size < 1:
+        raise ValueError(f"{what}: offsets need n + 1 entries")
+    if off.size > 1 and bool(np.any(off[1:] < off[:-1])):
+        raise ValueError(f"{what}: offsets must not decrease")
+    _need(data, int(off[-1]), what)
+    return int(off.size) - 1
+
+
 def pack(items) -> tuple[np.ndarray, np.ndarray]:
     """list of bytes-like -> (packed u8, u64 offsets[n+1])."""
     off = np.zeros(len(items) + 1, dtype=np.uint64)
@@ -109,21 +126,25 @@ class Engine:
     # =================================================================================
     def sha3(self, data, off, d: int) -> np.ndarray:
         data, off = _u8(data), _u64(off)
-        n = len(off) - 1
+        n = _need_packed(data, off, "sha3 messages")
         out = np.zeros((n, max(d // 8, 0) if d in (224, 256, 384, 512) else 1), dtype=np.uint8)
         self._check(self.lib.capy_sha3_batch(self._ctx, d, _hp(data), _hp(off), n, _hp(out), 0))
         return out
 
     def sha3_fixed(self, data, msg_len: int, stride: int, n: int, d: int, out: np.ndarray | None = None) -> np.ndarray:
         data = _u8(data)
+        if n:
+            _need(data, (n - 1) * stride + msg_len, "sha3_fixed messages")
         if out is None:
             out = np.zeros((n, d // 8 if d in (224, 256, 384, 512) else 1), dtype=np.uint8)
+        elif d in (224, 256, 384, 512):
+            _need(out.reshape(-1), n * (d // 8), "sha3_fixed digests")
         self._check(self.lib.capy_sha3_batch_fixed(self._ctx, d, _hp(data), msg_len, stride, n, _hp(out), 0))
         return out
 
     def cshake(self, data, off, out_bits: int, fn: bytes, custom: bytes, d: int) -> np.ndarray:
         data, off = _u8(data), _u64(off)
-        n = len(off) - 1
+        n = _need_packed(data, off, "cshake messages")
         out = np.zeros((n, out_bits // 8), dtype=np.uint8)
         fn_a, cs_a = _u8(fn), _u8(custom)
         self._check(self.lib.capy_cshake_batch(self._ctx, d, _hp(data), _hp(off), n, _hp(fn_a), len(fn_a), _hp(cs_a),
@@ -132,13 +153,17 @@ class Engine:
 
     def kmac_xof(self, keys, key_off, data, off, out_bits: int, custom: bytes, d: int, out_off=None) -> np.ndarray:
         keys, key_off, data, off = _u8(keys), _u64(key_off), _u8(data), _u64(off)
-        n = len(off) - 1
+        n = _need_packed(data, off, "kmac messages")
+        if _need_packed(keys, key_off, "kmac keys") != n:
+            raise ValueError("kmac: keys and messages differ in count")
         cs_a = _u8(custom)
         if out_off is None:
             out = np.zeros((n, out_bits // 8), dtype=np.uint8)
             oo = None
         else:
             out_off = _u64(out_off)
+            if out_off.size != n + 1 or bool(np.any(out_off[1:] < out_off[:-1])):
+                raise ValueError("kmac: out_off needs n + 1 non-decreasing entries")
             out = np.zeros(int(out_off[-1]), dtype=np.uint8)
             oo = _hp(out_off)
         self._check(self.lib.capy_kmac_xof_batch(self._ctx, d, _hp(keys), _hp(key_off), _hp(data), _hp(off), n,
@@ -148,14 +173,21 @@ class Engine:
     def ed448_fixed_base(self, scalars_be56, out: np.ndarray | None = None) -> np.ndarray:
         sc = _u8(scalars_be56)
         n = len(sc) // 56
+        _need(sc, n * 56, "scalars")
+        if len(sc) != n * 56:
+            raise ValueError("scalars: length is not a multiple of 56")
         if out is None:
             out = np.zeros((n, 112), dtype=np.uint8)
+        else:
+            _need(out.reshape(-1), n * 112, "fixed_base output")
         self._check(self.lib.capy_ed448_fixed_base_batch(self._ctx, _hp(sc), n, _hp(out)))
         return out
 
     def ed448_var_base(self, scalars_be56, points_xy112) -> tuple[int, np.ndarray]:
         sc, pts = _u8(scalars_be56), _u8(points_xy112)
         n = len(sc) // 56
+        if len(sc) != n * 56 or len(pts) != n * 112:
+            raise ValueError(f"var_base: {len(sc)} scalar bytes / {len(pts)} point bytes are not n x 56 / n x 112")
         out = np.zeros((n, 112), dtype=np.uint8)
         rc = self._check(self.lib.capy_ed448_var_base_batch(self._ctx, _hp(sc), _hp(pts), n, _hp(out)),
                          allow=(B.ERR_BAD_POINT,))
@@ -163,14 +195,16 @@ class Engine:
 
     def ed448_keygen(self, pws, pw_off, d: int) -> np.ndarray:
         pws, pw_off = _u8(pws), _u64(pw_off)
-        n = len(pw_off) - 1
+        n = _need_packed(pws, pw_off, "keygen passwords")
         out = np.zeros((n, 112), dtype=np.uint8)
         self._check(self.lib.capy_ed448_keygen_batch(self._ctx, d, _hp(pws), _hp(pw_off), n, _hp(out)))
         return out
 
     def ed448_sign(self, pws, pw_off, msgs, msg_off, d: int) -> tuple[np.ndarray, np.ndarray]:
         pws, pw_off, msgs, msg_off = _u8(pws), _u64(pw_off), _u8(msgs), _u64(msg_off)
-        n = len(pw_off) - 1
+        n = _need_packed(pws, pw_off, "sign passwords")
+        if _need_packed(msgs, msg_off, "sign messages") != n:
+            raise ValueError("sign: passwords and messages differ in count")
         h = np.zeros((n, 56), dtype=np.uint8)
         z = np.zeros((n, 56), dtype=np.uint8)
         self._check(self.lib.capy_ed448_sign_batch(self._ctx, d, _hp(pws), _hp(pw_off), _hp(msgs), _hp(msg_off), n,
@@ -179,7 +213,9 @@ class Engine:
 
     def ed448_verify(self, pub_xy112, msgs, msg_off, h56, z_be56, d: int) -> tuple[int, np.ndarray]:
         pub, msgs, msg_off, h, z = _u8(pub_xy112), _u8(msgs), _u64(msg_off), _u8(h56), _u8(z_be56)
-        n = len(msg_off) - 1
+        n = _need_packed(msgs, msg_off, "verify messages")
+        if len(pub) != n * 112 or len(h) != n * 56 or len(z) != n * 56:
+            raise ValueError(f"verify: pub/h/z hold {len(pub)}/{len(h)}/{len(z)} bytes, need {n} x 112/56/56")
         ok = np.zeros(n, dtype=np.uint8)
         rc = self._check(self.lib.capy_ed448_verify_batch(self._ctx, d, _hp(pub), _hp(msgs), _hp(msg_off), _hp(h),
                                                           _hp(z), n, _hp(ok)), allow=(B.ERR_BAD_POINT,))
@@ -188,6 +224,8 @@ class Engine:
     def ed448_ecdh(self, k_rand56, pub_xy112, want_z: bool = True):
         k, pub = _u8(k_rand56), _u8(pub_xy112)
         n = len(k) // 56
+        if len(k) != n * 56 or len(pub) != n * 112:
+            raise ValueError(f"ecdh: {len(k)} nonce bytes / {len(pub)} key bytes are not n x 56 / n x 112")
         wx = np.zeros((n, 56), dtype=np.uint8)
         z = np.zeros((n, 112), dtype=np.uint8) if want_z else None
         rc = self._check(self.lib.capy_ed448_ecdh_batch(self._ctx, _hp(k), _hp(pub), n, _hp(wx), _hp(z)),
@@ -197,7 +235,9 @@ class Engine:
     def sponge_encrypt(self, pws, pw_off, nonces, nonce_len: int, msgs, msg_off, d: int, variant: int = B.AE_SHA3):
         """-> (ciphertext packed like msgs, tags n x 64)."""
         pws, pw_off, nonces, msgs, msg_off = _u8(pws), _u64(pw_off), _u8(nonces), _u8(msgs), _u64(msg_off)
-        n = len(msg_off) - 1
+        n = _need_packed(msgs, msg_off, "sponge_encrypt messages")
+        if _need_packed(pws, pw_off, "sponge_encrypt passwords") != n or len(nonces) != n * nonce_len:
+            raise ValueError(f"sponge_encrypt: need {n} passwords and {n} x {nonce_len} nonce bytes")
         ct = np.zeros(len(msgs), dtype=np.uint8)
         tag = np.zeros((n, 64), dtype=np.uint8)
         self._check(self.lib.capy_sponge_encrypt_batch(self._ctx, d, variant, _hp(pws), _hp(pw_off), _hp(nonces), nonce_len,
@@ -207,7 +247,9 @@ class Engine:
     def sponge_decrypt(self, pws, pw_off, nonces, nonce_len: int, ct, ct_off, tags, d: int, variant: int = B.AE_SHA3):
         """-> (buffer packed like ct, ok n)."""
         pws, pw_off, nonces, ct, ct_off, tags = _u8(pws), _u64(pw_off), _u8(nonces), _u8(ct), _u64(ct_off), _u8(tags)
-        n = len(ct_off) - 1
+        n = _need_packed(ct, ct_off, "sponge_decrypt ciphertexts")
+        if _need_packed(pws, pw_off, "sponge_decrypt passwords") != n or len(nonces) != n * nonce_len or len(tags) != n * 64:
+            raise ValueError(f"sponge_decrypt: need {n} passwords, {n} x {nonce_len} nonce bytes and {n} x 64 tag bytes")
         out = np.zeros(len(ct), dtype=np.uint8)
         ok = np.zeros(n, dtype=np.uint8)
         self._check(self.lib.capy_sponge_decrypt_batch(self._ctx, d, variant, _hp(pws), _hp(pw_off), _hp(nonces), nonce_len,
@@ -217,7 +259,9 @@ class Engine:
     def ed448_key_encrypt(self, pub_xy112, k_rand56, msgs, msg_off, d: int):
         """-> (rc, ciphertext, tags n x 56, nonce points Z n x 112)."""
         pub, k, msgs, msg_off = _u8(pub_xy112), _u8(k_rand56), _u8(msgs), _u64(msg_off)
-        n = len(msg_off) - 1
+        n = _need_packed(msgs, msg_off, "key_encrypt messages")
+        if len(pub) != n * 112 or len(k) != n * 56:
+            raise ValueError(f"key_encrypt: pub/k hold {len(pub)}/{len(k)} bytes, need {n} x 112/56")
         ct = np.zeros(len(msgs), dtype=np.uint8)
         tag = np.zeros((n, 56), dtype=np.uint8)
         z = np.zeros((n, 112), dtype=np.uint8)
@@ -228,7 +272,9 @@ class Engine:
     def ed448_key_decrypt(self, pws, pw_off, z_xy112, ct, ct_off, tags, d: int):
         """-> (rc, buffer packed like ct, ok n)."""
         pws, pw_off, z, ct, ct_off, tags = _u8(pws), _u64(pw_off), _u8(z_xy112), _u8(ct), _u64(ct_off), _u8(tags)
-        n = len(ct_off) - 1
+        n = _need_packed(ct, ct_off, "key_decrypt ciphertexts")
+        if _need_packed(pws, pw_off, "key_decrypt passwords") != n or len(z) != n * 112 or len(tags) != n * 56:
+            raise ValueError(f"key_decrypt: need {n} passwords, {n} x 112 nonce-point bytes and {n} x 56 tag bytes")
         out = np.zeros(len(ct), dtype=np.uint8)
         ok = np.zeros(n, dtype=np.uint8)
         rc = self._check(self.lib.capy_ed448_key_decrypt_batch(self._ctx, d, _hp(pws), _hp(pw_off), _hp(z), _hp(ct),

@@ -77,17 +77,29 @@ void host_fixed_base(const uint8_t* k_be, int constant_time, uint8_t* out_xy) {
   pt_fixed_base_mul(r, kr, table(), constant_time != 0);
   pt_out(out_xy, r);
 }
+int host_var_base2(const uint8_t* k_be, const uint8_t* pt_xy, int constant_time, const uint8_t* addend_xy, uint8_t* out_xy);
 int host_var_base(const uint8_t* k_be, const uint8_t* pt_xy, int constant_time, uint8_t* out_xy) {
+  return host_var_base2(k_be, pt_xy, constant_time, nullptr, out_xy);
+}
+// [k]P (+ addend): the body of var_base_kernel with the per-item table on the heap (stride 3 between chunks, to
+// exercise the interleaving arithmetic)
+int host_var_base2(const uint8_t* k_be, const uint8_t* pt_xy, int constant_time, const uint8_t* addend_xy, uint8_t* out_xy) {
   Sc k;
   sc_from_be(k, k_be);
   Fe x, y;
   fe_from_le56(x, pt_xy);
   fe_from_le56(y, pt_xy + 56);
-  PtExt p, r;
-  if (!pt_from_affine(p, x, y)) return -4;
-  PtCached tab[8];
-  int8_t dig[113];
-  pt_var_base_mul(r, k, p, tab, dig, constant_time != 0);
+  PtExt r;
+  if (!pt_from_affine(r, x, y)) return -4;
+  constexpr int STRIDE = 3;
+  std::vector<uint4> tab((size_t)VB_ENTRIES * VB_CHUNKS * STRIDE);
+  PtExt add;
+  if (addend_xy) {
+    fe_from_le56(x, addend_xy);
+    fe_from_le56(y, addend_xy + 56);
+    if (!pt_from_affine(add, x, y)) return -4;
+  }
+  pt_var_base_mul<STRIDE>(r, k, tab.data() + 1, constant_time != 0, addend_xy != nullptr, [&](PtExt& a) { a = add; });
   pt_out(out_xy, r);
   return 0;
 }

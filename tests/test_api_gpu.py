@@ -77,3 +77,55 @@ def test_scrub_keeps_the_ctx_usable(gpu):
     gpu.compute_sha3_hash(m2, SecParam.D256)
     assert [x.digest for x in m2] == first
     assert [k.pub_key for k in gpu.new_keypairs([b"pw1", b"pw2"], "k", SecParam.D512)] == [k.pub_key for k in keys]
+
+
+def test_one_malformed_signature_fails_alone(gpu):
+    """A signature whose h is not 56 bytes (or a key that is not 112) fails on its own; the fixed-stride batch the
+    C side sees is built from the well-formed items only, so their verdicts do not shift."""
+    from capycrypt_b200.api import Signature
+
+    rnd = random.Random(7)
+    pws = [rnd.randbytes(16) for _ in range(6)]
+    keys = gpu.new_keypairs(pws, "k", SecParam.D256)
+    msgs = [Message.new(rnd.randbytes(40 + i)) for i in range(6)]
+    gpu.sign(msgs, keys, SecParam.D256)
+    pubs = [k.pub_key for k in keys]
+    msgs[1].sig = Signature(h=msgs[1].sig.h[:55], z=msgs[1].sig.z)
+    msgs[3].sig = Signature(h=msgs[3].sig.h, z=msgs[3].sig.z + b"\0")
+    pubs[4] = pubs[4][:111]
+    res = gpu.verify(msgs, pubs)
+    assert [r is None for r in res] == [True, False, True, False, False, True]
+    assert all(r.kind == "SignatureVerificationFailure" for r in res if r is not None)
+
+
+def test_engine_refuses_short_buffers(engine):
+    """The C ABI trusts (pointer, n): the array front end checks n * stride before every call."""
+    import numpy as np
+
+    from capycrypt_b200 import pack
+
+    md, mo = pack([b"abc", b"defg"])
+    with pytest.raises(ValueError):
+        engine.ed448_verify(np.zeros(112, np.uint8), md, mo, np.zeros(112, np.uint8), np.zeros(112, np.uint8), 256)
+    with pytest.raises(ValueError):
+        engine.ed448_var_base(np.zeros(56, np.uint8), np.zeros(100, np.uint8))
+    with pytest.raises(ValueError):
+        engine.sha3(md[:5], mo, 256)
+    with pytest.raises(ValueError):
+        engine.sponge_decrypt(*pack([b"p", b"q"]), np.zeros(1000, np.uint8), 512, md, mo, np.zeros(128, np.uint8), 256)
+    with pytest.raises(ValueError):
+        engine.ed448_key_decrypt(*pack([b"p", b"q"]), np.zeros(224, np.uint8), md, mo, np.zeros(56, np.uint8), 256)
+
+
+def test_key_decrypt_with_malformed_nonce_point_fails_alone(gpu):
+    rnd = random.Random(8)
+    pws = [rnd.randbytes(12) for _ in range(3)]
+    keys = gpu.new_keypairs(pws, "k", SecParam.D512)
+    plain = [rnd.randbytes(30 + i) for i in range(3)]
+    msgs = [Message.new(p) for p in plain]
+    gpu.key_encrypt(msgs, [k.pub_key for k in keys], SecParam.D512)
+    ct1 = bytes(msgs[1].msg)
+    msgs[1].asym_nonce = msgs[1].asym_nonce[:100]
+    res = gpu.key_decrypt(msgs, pws)
+    assert res[0] is None and res[2] is None and res[1].kind == "KeyDecryptionError"
+    assert bytes(msgs[0].msg) == plain[0] and bytes(msgs[2].msg) == plain[2] and bytes(msgs[1].msg) == ct1

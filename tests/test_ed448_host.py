@@ -128,3 +128,16 @@ def test_var_base_including_small_order_and_unreduced(host):
                 assert host.host_var_base(k.to_bytes(56, "big"), E.point_to_bytes(pt), ct, out) == 0
                 assert bytes(out) == E.point_to_bytes(E.scalar_mult(k, pt)), (k, pt, ct)
     assert host.host_var_base((5).to_bytes(56, "big"), E.point_to_bytes((5, 7)), 1, out) == -4
+
+
+def test_var_base_with_addend(host):
+    """The verify shape U = [z]G + [h]V (ecc/signable.rs:77): the addend is the last iteration of the ladder loop."""
+    rnd = random.Random(6)
+    out = (C.c_uint8 * 112)()
+    for _ in range(6):
+        pt = E.scalar_mult(rnd.randrange(R), E.GENERATOR)
+        add = rnd.choice([E.IDENTITY, pt, E.scalar_mult(rnd.randrange(R), E.GENERATOR), (0, P - 1)])
+        k = rnd.choice([0, 1, 2**448 - 1, rnd.randrange(2**448)])
+        for ct in (0, 1):
+            assert host.host_var_base2(k.to_bytes(56, "big"), E.point_to_bytes(pt), ct, E.point_to_bytes(add), out) == 0
+            assert bytes(out) == E.point_to_bytes(E.point_add(E.scalar_mult(k, pt), add)), (k, pt, add, ct)
