@@ -32,6 +32,12 @@ N_ROT = 4  # rotating input/output buffers: 4 x (64 + 32) MiB = 384 MiB > 126 MB
 OPS_PER_PERM = 4320  # 122 LOP3 + 58 SHF per round x 24
 MAC_FIXED = 2.03e5  # canonical 32x32->64 MAC budgets per scalar multiplication
 MAC_VAR = 7.12e5
+# IMAD.WIDE instructions the kernels actually execute per scalar multiplication (SASS counts x trip counts):
+# fixed base = 90 mixed additions x 7 M + dual isogeny + scalar glue on the isogenous curve; variable base =
+# 448 x (4 S + 3 M) + 112 M + 113 x 9 M + table (1 dbl + 6 add), M = 193, S = 110
+MAC_EXEC_FIXED = 1.23e5
+MAC_EXEC_VAR = 6.86e5
+WARP_TIER_US_PER_PERM = 2.19  # chain speed of the fastest tier (one warp per message), profiles/README.md
 PEAK_FALLBACK = {"lop3": 18.52e12, "imad_wide": 8.67e12}  # profiles/r01_peaks_int_pipes.json
 
 
@@ -457,10 +463,24 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     assert h_out[:DIGEST].tobytes() == hashlib.sha3_256(m0).digest()
-    e2e = {"value": world * N_MSGS * MSG_LEN * k_e2e / e2e_s / 1e9, "unit": "GB/s",
+    # the denominator of the end-to-end number: the same bytes, the same pinned buffers, every rank at the same time,
+    # plain cudaMemcpyAsync in both directions and no kernel (capy_copy_probe)
+    if dist:
+        dist.barrier()
+    link_ms = eng.copy_probe(h_in, h_out, reps=10)
+    if dist:
+        t = torch.tensor([link_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        link_ms = float(t.item())
+    e2e_val = world * N_MSGS * MSG_LEN * k_e2e / e2e_s / 1e9
+    link_ceiling = world * N_MSGS * MSG_LEN / (link_ms * 1e-3) / 1e9
+    e2e = {"value": e2e_val, "unit": "GB/s",
            "h2d_bytes_per_step": N_MSGS * MSG_LEN, "d2h_bytes_per_step": N_MSGS * DIGEST, "steps": k_e2e,
            "ms_per_step": e2e_s / k_e2e * 1e3,
            "api": "capy_sha3_batch_fixed (host buffers from capy_host_alloc, chunked H2D/kernel/D2H on 3 streams)",
+           "link_ceiling_GBps": link_ceiling, "link_ms_per_step": link_ms, "frac_of_link": e2e_val / link_ceiling,
+           "link_probe": "capy_copy_probe: 64 MiB H2D + 32 MiB D2H per rank from the same pinned buffers, both directions "
+                         "overlapped, all ranks concurrently, no kernel (max over ranks)",
            "host_numa_binding": numa}
 
     # ---- roofline of the dominant kernel (sha3_short_kernel<17, 8>: one launch per step) ----
@@ -513,9 +533,41 @@ def main():
         emit_json_line(line)
 
 
+def lpt_shards(lens, world):
+    """Longest-processing-time-first assignment of messages to ranks: every message goes, longest first, to
+    the rank with the least work so far.  Returns a list of index arrays, one per rank."""
+    import heapq
+
+    import numpy as np
+
+    order = np.argsort(-lens, kind="stable")
+    heap = [(0, r) for r in range(world)]
+    shards = [[] for _ in range(world)]
+    for i in order:
+        load, r = heapq.heappop(heap)
+        shards[r].append(int(i))
+        heapq.heappush(heap, (load + int(lens[i]) // 72 + 2, r))
+    return [np.sort(np.array(sh, dtype=np.int64)) for sh in shards]
+
+
+def _oracle():
+    """The checker (oracle/ref_cpu.c) for the sampled parity checks of the extras -- outside every timed region."""
+    from oracle import cpu
+
+    return cpu.get()
+
+
 def extras(eng, dev, peaks, world, dist, rank):
-    """Side measurements for the other BASELINE.json configs (device-resident, CUDA events, max over ranks)."""
+    """Side measurements for the other BASELINE.json configs (device-resident, CUDA events, max over ranks), each
+    followed -- outside its timed region -- by a check of a seeded sample of its results against the C oracle, and
+    host-buffer (e2e) figures for cfg 2, 4 and 5 through the blocking C entry points with pinned buffers."""
+    import time as _t
+
+    import numpy as np
     import torch
+
+    orc = _oracle()
+    eng.set_plan_cache(True)  # ragged _dev calls that pass the same offsets array again launch without a host round trip
 
     def timed(fn, steps, warmup=2):
         for _ in range(warmup):
@@ -536,20 +588,47 @@ def extras(eng, dev, peaks, world, dist, rank):
             ms = float(t.item())
         return ms
 
+    def timed_host(fn, steps, warmup=1):
+        for _ in range(warmup):
+            fn()
+        if dist:
+            dist.barrier()
+        t0 = _t.perf_counter()
+        for _ in range(steps):
+            fn()
+        dt = (_t.perf_counter() - t0) / steps
+        if dist:
+            t = torch.tensor([dt], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        return dt
+
+    def rows(t, n, w, idx):  # sample rows of a device tensor as one packed numpy array
+        return t.view(n, w)[torch.from_numpy(idx).to(dev)].cpu().numpy().reshape(-1)
+
     g = torch.Generator(device=dev)
     g.manual_seed(100 + rank)
     rnd = lambda n: torch.randint(0, 256, (n,), dtype=torch.uint8, device=dev, generator=g)
+    rs_np = np.random.default_rng(1000 + rank)
     out = {}
+    NS = 256  # oracle sample per check
 
-    # cfg 2: KMACXOF256 (D512) over 2^16 x 4 KB messages, 32-byte keys, 512-bit output
+    # ---- cfg 2: KMACXOF256 (D512) over 2^16 x 4 KB messages, 32-byte keys, 512-bit output --------------------------
     n2, mlen = 1 << 16, 4096
     data, keys = rnd(n2 * mlen), rnd(n2 * 32)
     o = torch.zeros(n2 * 64, dtype=torch.uint8, device=dev)
-    ms = timed(lambda: eng.kmac_xof_fixed_dev(keys, 32, 32, data, mlen, mlen, n2, 512, b"My Tagged Application", 512, o), 10)
+    custom = b"My Tagged Application"
+    ms = timed(lambda: eng.kmac_xof_fixed_dev(keys, 32, 32, data, mlen, mlen, n2, 512, custom, 512, o), 10)
+    idx2 = np.sort(rs_np.choice(n2, size=NS, replace=False))
+    s_data, s_keys = rows(data, n2, mlen, idx2), rows(keys, n2, 32, idx2)
+    s_off, s_koff = np.arange(NS + 1, dtype=np.uint64) * mlen, np.arange(NS + 1, dtype=np.uint64) * 32
+    assert np.array_equal(rows(o, n2, 64, idx2).reshape(NS, 64),
+                          orc.kmac_xof_batch(s_keys, s_koff, s_data, s_off, 512, custom, 512)), "cfg 2: KMACXOF256 != oracle"
     perms = 32  # 33 absorbed blocks, the constant prefix block is cached
     out["kmac256_2^16x4KB"] = {
         "GBps": world * n2 * mlen / (ms * 1e-3) / 1e9, "ms_per_step": ms,
-        "frac_int_alu": n2 * perms * OPS_PER_PERM / (ms * 1e-3) / peaks["lop3"], "perms_per_msg": perms}
+        "frac_int_alu": n2 * perms * OPS_PER_PERM / (ms * 1e-3) / peaks["lop3"], "perms_per_msg": perms,
+        "oracle_sample": NS}
 
     # cfg 2, variable-length squeeze: cSHAKE256 and KMACXOF256 with a 4 096-byte output per message (the keystream shape of
     # sha3/encryptable.rs:41), and FIPS 202 SHAKE256 (no reference counterpart) with a 64-byte output
@@ -557,8 +636,17 @@ def extras(eng, dev, peaks, world, dist, rank):
     koff2 = torch.arange(n2 + 1, dtype=torch.int64, device=dev) * 32
     big = torch.zeros(n2 * 4096, dtype=torch.uint8, device=dev)
     ms_c = timed(lambda: eng.cshake_dev(data, off2, 8 * 4096, b"", b"Email Signature", 512, big), 5)
-    ms_k = timed(lambda: eng.kmac_xof_dev(keys, koff2, data, off2, 8 * 4096, b"My Tagged Application", 512, big), 5)
+    assert np.array_equal(rows(big, n2, 4096, idx2[:32]).reshape(32, 4096),
+                          orc.cshake_batch(s_data[: 32 * mlen], s_off[:33], 8 * 4096, b"", b"Email Signature", 512)), "cSHAKE256 != oracle"
+    ms_k = timed(lambda: eng.kmac_xof_dev(keys, koff2, data, off2, 8 * 4096, custom, 512, big), 5)
+    assert np.array_equal(rows(big, n2, 4096, idx2[:32]).reshape(32, 4096),
+                          orc.kmac_xof_batch(s_keys[: 32 * 32], s_koff[:33], s_data[: 32 * mlen], s_off[:33], 8 * 4096, custom, 512)), \
+        "KMACXOF256 (4 KB out) != oracle"
     ms_s = timed(lambda: eng.fips_shake_dev(data, off2, 256, 64, o), 5)
+    import hashlib
+
+    m0 = data[:mlen].cpu().numpy().tobytes()
+    assert o[:64].cpu().numpy().tobytes() == hashlib.shake_256(m0).digest(64), "FIPS SHAKE256 != hashlib"
     sq = (4096 + 135) // 136 - 1  # extra permutations of a 4 096-byte squeeze at rate 136
     out["cfg2_variable_squeeze_2^16x4KB"] = {
         "cshake256_out4096B_ms": ms_c, "cshake256_out4096B_GBps_in_plus_out": world * n2 * (mlen + 4096) / (ms_c * 1e-3) / 1e9,
@@ -568,19 +656,33 @@ def extras(eng, dev, peaks, world, dist, rank):
         "fips_shake256_frac_int_alu": n2 * 31 * OPS_PER_PERM / (ms_s * 1e-3) / peaks["lop3"]}
     del big
 
-    # cfg 5: mixed-size SHA3-512, lengths log-uniform in [64 B, 1 MiB], 16 GiB in total (strong scaling: the
-    # 16 GiB are split over the ranks); longest-message-first schedule, one thread per message
-    import numpy as np
+    # cfg 2 end to end: host buffers (pinned, capy_host_alloc) through capy_kmac_xof_batch, H2D of keys + messages +
+    # offsets and D2H of the tags inside the timed region
+    h_data, h_keys = eng.pinned(n2 * mlen), eng.pinned(n2 * 32)
+    h_data[:] = data.cpu().numpy()
+    h_keys[:] = keys.cpu().numpy()
+    np_off, np_koff = np.arange(n2 + 1, dtype=np.uint64) * mlen, np.arange(n2 + 1, dtype=np.uint64) * 32
+    res = {}
+    dt = timed_host(lambda: res.__setitem__("t", eng.kmac_xof(h_keys, np_koff, h_data, np_off, 512, custom, 512)), 3)
+    assert np.array_equal(res["t"][idx2], rows(o.new_tensor(res["t"].reshape(-1)) if False else torch.from_numpy(res["t"].reshape(-1)).to(dev), n2, 64, idx2).reshape(NS, 64))
+    assert np.array_equal(res["t"][idx2], orc.kmac_xof_batch(s_keys, s_koff, s_data, s_off, 512, custom, 512)), "cfg 2 e2e != oracle"
+    out["kmac256_2^16x4KB"]["e2e"] = {
+        "GBps": world * n2 * mlen / dt / 1e9, "ms_per_step": dt * 1e3, "h2d_bytes_per_step": n2 * (mlen + 32 + 16),
+        "d2h_bytes_per_step": n2 * 64, "api": "capy_kmac_xof_batch (pinned host buffers from capy_host_alloc)"}
+    del h_data, h_keys
 
+    # ---- cfg 5: mixed-size SHA3-512, lengths log-uniform in [64 B, 1 MiB], 16 GiB in total (strong scaling: the 16 GiB
+    # are split over the ranks longest-first, LPT); one launch, three tiers ------------------------------------------
     rs = np.random.default_rng(5)
-    total = (16 << 30) // world
+    total = 16 << 30
     lens, acc = [], 0
-    while acc < total * world:
+    while acc < total:
         c = np.exp(rs.uniform(np.log(64), np.log(1 << 20), size=8192)).astype(np.int64)
         lens.append(c)
         acc += int(c.sum())
-    lens = np.concatenate(lens)
-    lens = lens[: int(np.searchsorted(np.cumsum(lens), total * world)) + 1][rank::world]  # this rank's share
+    lens_all = np.concatenate(lens)
+    lens_all = lens_all[: int(np.searchsorted(np.cumsum(lens_all), total)) + 1]
+    lens = lens_all[lpt_shards(lens_all, world)[rank]] if world > 1 else lens_all
     off5 = np.zeros(len(lens) + 1, np.int64)
     off5[1:] = np.cumsum(lens)
     nbytes5 = int(off5[-1])
@@ -589,45 +691,95 @@ def extras(eng, dev, peaks, world, dist, rank):
     t_off5 = torch.from_numpy(off5).to(dev)
     o5 = torch.zeros(len(lens) * 64, dtype=torch.uint8, device=dev)
     ms = timed(lambda: eng.sha3_dev(d5, t_off5, 512, o5), 2, 1)
+    # sampled oracle check: every quirk length in a window, the longest (fast-tier) messages, random others
+    quirk = np.nonzero((lens % 72 == 71) | (lens % 136 == 135))[0][:64]
+    pick = np.unique(np.concatenate([quirk, np.argsort(lens)[-8:], rs_np.choice(len(lens), size=NS, replace=False)]))
+    d5_np = [d5[int(off5[i]):int(off5[i + 1])].cpu().numpy() for i in pick]
+    s5_off = np.zeros(len(pick) + 1, np.uint64)
+    s5_off[1:] = np.cumsum([len(x) for x in d5_np])
+    assert np.array_equal(o5.view(len(lens), 64)[torch.from_numpy(pick).to(dev)].cpu().numpy(),
+                          orc.sha3_batch(np.concatenate(d5_np), s5_off, 512, threads=0)), "cfg 5: SHA3-512 != oracle"
+    del d5_np
     # A/B: the same batch with one thread per message everywhere (CAPY_FLAG_NO_PAIR = 2)
     ms_solo = timed(lambda: eng._check(eng.lib.capy_sha3_batch_dev(eng._ctx, 0, eng._stream(), 512, d5.data_ptr(),
                                                                    t_off5.data_ptr(), len(lens), o5.data_ptr(), 2)), 1, 1)
     perms5 = int(((lens + 1 + 71) // 72).sum())
+    longest = int((lens.max() + 1 + 71) // 72)
     tot_bytes = torch.tensor([float(nbytes5)], device=dev, dtype=torch.float64)
     tot_perms = torch.tensor([float(perms5)], device=dev, dtype=torch.float64)
+    max_chain = torch.tensor([float(longest)], device=dev, dtype=torch.float64)
+    max_perms = torch.tensor([float(perms5)], device=dev, dtype=torch.float64)
     if dist:
         dist.all_reduce(tot_bytes)
         dist.all_reduce(tot_perms)
+        dist.all_reduce(max_chain, op=dist.ReduceOp.MAX)
+        dist.all_reduce(max_perms, op=dist.ReduceOp.MAX)
+    chain_floor_ms = float(max_chain.item()) * WARP_TIER_US_PER_PERM * 1e-3
+    work_floor_ms = float(max_perms.item()) * OPS_PER_PERM / peaks["lop3"] * 1e3
+    floor_ms = max(chain_floor_ms, work_floor_ms)
     out["sha3_512_mixed_16GiB"] = {
         "GBps": float(tot_bytes.item()) / (ms * 1e-3) / 1e9, "ms_per_step": ms, "msgs_this_rank": int(len(lens)),
         "frac_int_alu": float(tot_perms.item()) / world * OPS_PER_PERM / (ms * 1e-3) / peaks["lop3"],
-        "scaling": "strong", "longest_chain_perms": int((lens.max() + 1 + 71) // 72),
-        "ms_one_thread_per_message": ms_solo,
-        "note": "a sponge is sequential per message: the step cannot be shorter than the longest message's chain "
-                "(1 MiB = 14 564 permutations: 67 ms with one thread per message, 52 ms with two threads, 32 ms with a "
-                "whole warp per message -- the tiers the longest messages of a chain-bound batch run in)"}
+        "scaling": "strong", "sharding": "LPT over all messages by permutation count (longest first to the least loaded rank)",
+        "longest_chain_perms": longest, "chain_floor_ms": chain_floor_ms, "work_floor_ms": work_floor_ms,
+        "frac_of_floor": floor_ms / ms, "ms_one_thread_per_message": ms_solo, "oracle_sample": int(len(pick)),
+        "note": "a sponge is sequential per message: the step cannot be shorter than the longest message's chain at the "
+                "fastest tier (1 MiB = 14 564 permutations x 2.19 us with a whole warp per message = chain_floor_ms) nor than "
+                "the rank's permutations at the ALU peak (work_floor_ms); frac_of_floor = max of the two / measured"}
     del d5, o5, t_off5
 
-    # cfg 3: Ed448 fixed-base [s]G for 2^20 scalars
+    # cfg 5 end to end: a 2 GiB shard (the share of one rank of an 8-GPU run) from pinned host memory through capy_sha3_batch
+    lens_e = lens_all[lpt_shards(lens_all, 8)[rank % 8]]
+    off_e = np.zeros(len(lens_e) + 1, np.uint64)
+    off_e[1:] = np.cumsum(lens_e)
+    nb_e = int(off_e[-1])
+    h5 = eng.pinned(nb_e)
+    blk = rs_np.integers(0, 256, size=64 << 20, dtype=np.uint8)
+    for p0 in range(0, nb_e, len(blk)):
+        h5[p0:p0 + len(blk)] = blk[: min(len(blk), nb_e - p0)]
+    dt = timed_host(lambda: res.__setitem__("d", eng.sha3(h5, off_e, 512)), 2)
+    pick = np.unique(np.concatenate([np.argsort(lens_e)[-4:], rs_np.choice(len(lens_e), size=NS, replace=False)]))
+    sm = [h5[int(off_e[i]):int(off_e[i + 1])] for i in pick]
+    s_o = np.zeros(len(pick) + 1, np.uint64)
+    s_o[1:] = np.cumsum([len(x) for x in sm])
+    assert np.array_equal(res["d"][pick], orc.sha3_batch(np.concatenate(sm), s_o, 512, threads=0)), "cfg 5 e2e != oracle"
+    out["sha3_512_mixed_16GiB"]["e2e_2GiB_shard"] = {
+        "GBps": world * nb_e / dt / 1e9, "ms_per_step": dt * 1e3, "bytes": nb_e, "msgs": int(len(lens_e)),
+        "h2d_bytes_per_step": nb_e + 8 * (len(lens_e) + 1), "d2h_bytes_per_step": 64 * len(lens_e),
+        "api": "capy_sha3_batch (pinned host buffers from capy_host_alloc; one rank's LPT shard of the 8-GPU run)"}
+    del h5, sm
+
+    # ---- cfg 3: Ed448 fixed-base [s]G for 2^20 scalars ------------------------------------------------------------
     n3 = 1 << 20
     sc = rnd(n3 * 56)
     pts = torch.zeros(n3 * 112, dtype=torch.uint8, device=dev)
     ms = timed(lambda: eng.ed448_fixed_base_dev(sc, n3, pts), 3, 1)
+    idx3 = np.sort(rs_np.choice(n3, size=NS, replace=False))
+    assert np.array_equal(rows(pts, n3, 112, idx3).reshape(NS, 112), orc.fixed_base_batch(rows(sc, n3, 56, idx3), threads=0)), \
+        "cfg 3: [s]G != oracle"
     rate = n3 / (ms * 1e-3)
     out["ed448_fixed_base_2^20"] = {
         "scalar_mults_per_s": world * rate, "ms_per_step": ms, "frac_imad_wide": rate * MAC_FIXED / peaks["imad_wide"],
-        "canonical_macs": MAC_FIXED, "constant_time_lookup": True}
+        "canonical_macs": MAC_FIXED, "executed_imad_wide": MAC_EXEC_FIXED,
+        "frac_imad_wide_executed": rate * MAC_EXEC_FIXED / peaks["imad_wide"], "constant_time_lookup": True, "oracle_sample": NS,
+        "note": "frac_imad_wide = canonical-budget MACs/s / IMAD.WIDE peak (comparable across designs; can exceed the pipe's "
+                "real utilisation because the comb on the isogenous curve executes fewer MACs); frac_imad_wide_executed = "
+                "IMAD.WIDE instructions actually issued / peak"}
 
     # variable base for 2^18 (scalar, point) pairs
     n4 = 1 << 18
     o4 = torch.zeros(n4 * 112, dtype=torch.uint8, device=dev)
     ms = timed(lambda: eng.ed448_var_base_dev(sc, pts, n4, o4), 2, 1)
+    idx4 = np.sort(rs_np.choice(n4, size=NS, replace=False))
+    rc_o, want = orc.var_base_batch(rows(sc, n3, 56, idx4), rows(pts, n3, 112, idx4), threads=0)
+    assert rc_o == 0 and np.array_equal(rows(o4, n4, 112, idx4).reshape(NS, 112), want), "[k]P != oracle"
     rate = n4 / (ms * 1e-3)
     out["ed448_var_base_2^18"] = {
         "scalar_mults_per_s": world * rate, "ms_per_step": ms, "frac_imad_wide": rate * MAC_VAR / peaks["imad_wide"],
-        "canonical_macs": MAC_VAR, "constant_time_lookup": True}
+        "canonical_macs": MAC_VAR, "executed_imad_wide": MAC_EXEC_VAR,
+        "frac_imad_wide_executed": rate * MAC_EXEC_VAR / peaks["imad_wide"], "constant_time_lookup": True, "oracle_sample": NS}
 
-    # cfg 4: Schnorr sign + verify, 2^18 x (32-byte password, 256-byte message), D512
+    # ---- cfg 4: Schnorr sign + verify, 2^18 x (32-byte password, 256-byte message), D512 ---------------------------
     pw, msg = rnd(n4 * 32), rnd(n4 * 256)
     pw_off = torch.arange(n4 + 1, dtype=torch.int64, device=dev) * 32
     msg_off = torch.arange(n4 + 1, dtype=torch.int64, device=dev) * 256
@@ -638,10 +790,32 @@ def extras(eng, dev, peaks, world, dist, rank):
     ms_k = timed(lambda: eng.ed448_keygen_dev(pw, pw_off, 512, pub), 2, 1)
     ms_s = timed(lambda: eng.ed448_sign_dev(pw, pw_off, msg, msg_off, 512, h, z), 2, 1)
     ms_v = timed(lambda: eng.ed448_verify_dev(pub, msg, msg_off, h, z, 512, ok), 2, 1)
-    assert bool(ok.all().item()), "engine rejected its own signatures"
+    s_pw, s_msg = rows(pw, n4, 32, idx4), rows(msg, n4, 256, idx4)
+    s_po, s_mo = np.arange(NS + 1, dtype=np.uint64) * 32, np.arange(NS + 1, dtype=np.uint64) * 256
+    h_ref, z_ref = orc.sign_batch(s_pw, s_po, s_msg, s_mo, 512, threads=0)
+    assert np.array_equal(rows(pub, n4, 112, idx4).reshape(NS, 112), orc.keygen_batch(s_pw, s_po, 512, threads=0)), "cfg 4: keygen != oracle"
+    assert np.array_equal(rows(h, n4, 56, idx4).reshape(NS, 56), h_ref) and np.array_equal(rows(z, n4, 56, idx4).reshape(NS, 56), z_ref), \
+        "cfg 4: signatures != oracle"
+    assert bool(ok.all().item()), "cfg 4: the engine rejected its own signatures"
+    assert orc.verify_batch(rows(pub, n4, 112, idx4), s_msg, s_mo, h_ref.reshape(-1), z_ref.reshape(-1), 512, threads=0).all()
     out["ed448_schnorr_2^18x256B"] = {
         "keygens_per_s": world * n4 / (ms_k * 1e-3), "signs_per_s": world * n4 / (ms_s * 1e-3),
-        "verifies_per_s": world * n4 / (ms_v * 1e-3), "ms_keygen": ms_k, "ms_sign": ms_s, "ms_verify": ms_v}
+        "verifies_per_s": world * n4 / (ms_v * 1e-3), "ms_keygen": ms_k, "ms_sign": ms_s, "ms_verify": ms_v, "oracle_sample": NS}
+    # cfg 4 end to end: pinned host buffers through capy_ed448_sign_batch / capy_ed448_verify_batch
+    h_pw, h_msg = eng.pinned(n4 * 32), eng.pinned(n4 * 256)
+    h_pw[:] = pw.cpu().numpy()
+    h_msg[:] = msg.cpu().numpy()
+    np_po, np_mo = np.arange(n4 + 1, dtype=np.uint64) * 32, np.arange(n4 + 1, dtype=np.uint64) * 256
+    dt_s = timed_host(lambda: res.__setitem__("s", eng.ed448_sign(h_pw, np_po, h_msg, np_mo, 512)), 2)
+    h_h, h_z = res["s"]
+    h_pub = pub.cpu().numpy()
+    dt_v = timed_host(lambda: res.__setitem__("v", eng.ed448_verify(h_pub, h_msg, np_mo, h_h, h_z, 512)), 2)
+    assert res["v"][0] == 0 and res["v"][1].all() and np.array_equal(h_h[idx4], h_ref) and np.array_equal(h_z[idx4], z_ref), "cfg 4 e2e"
+    out["ed448_schnorr_2^18x256B"]["e2e"] = {
+        "signs_per_s": world * n4 / dt_s, "verifies_per_s": world * n4 / dt_v, "ms_sign": dt_s * 1e3, "ms_verify": dt_v * 1e3,
+        "h2d_bytes_per_sign": 32 + 256 + 16, "d2h_bytes_per_sign": 112, "h2d_bytes_per_verify": 112 + 256 + 8 + 112,
+        "d2h_bytes_per_verify": 1, "api": "capy_ed448_sign_batch / capy_ed448_verify_batch (pinned host buffers)"}
+    del h_pw, h_msg
     # the other message sizes SURVEY 8(d) asks for (64 B and 4 KB) and cfg 3's password variant (2^20 x 32-byte passwords)
     for mlen4 in (64, 4096):
         msg_b = rnd(n4 * mlen4)
@@ -649,6 +823,8 @@ def extras(eng, dev, peaks, world, dist, rank):
         ms_s2 = timed(lambda: eng.ed448_sign_dev(pw, pw_off, msg_b, off_b, 512, h, z), 2, 1)
         ms_v2 = timed(lambda: eng.ed448_verify_dev(pub, msg_b, off_b, h, z, 512, ok), 2, 1)
         assert bool(ok.all().item())
+        h_r2, z_r2 = orc.sign_batch(s_pw[: 32 * 32], s_po[:33], rows(msg_b, n4, mlen4, idx4[:32]), np.arange(33, dtype=np.uint64) * mlen4, 512, threads=0)
+        assert np.array_equal(rows(h, n4, 56, idx4[:32]).reshape(32, 56), h_r2) and np.array_equal(rows(z, n4, 56, idx4[:32]).reshape(32, 56), z_r2)
         out[f"ed448_schnorr_2^18x{mlen4}B"] = {"signs_per_s": world * n4 / (ms_s2 * 1e-3), "verifies_per_s": world * n4 / (ms_v2 * 1e-3),
                                                "ms_sign": ms_s2, "ms_verify": ms_v2}
         del msg_b, off_b
@@ -656,12 +832,16 @@ def extras(eng, dev, peaks, world, dist, rank):
     pw20_off = torch.arange(n3 + 1, dtype=torch.int64, device=dev) * 32
     pub20 = torch.zeros(n3 * 112, dtype=torch.uint8, device=dev)
     ms_k20 = timed(lambda: eng.ed448_keygen_dev(pw20, pw20_off, 512, pub20), 2, 1)
+    assert np.array_equal(rows(pub20, n3, 112, idx3[:64]).reshape(64, 112),
+                          orc.keygen_batch(rows(pw20, n3, 32, idx3[:64]), np.arange(65, dtype=np.uint64) * 32, 512, threads=0))
     out["ed448_keygen_2^20_passwords"] = {"keygens_per_s": world * n3 / (ms_k20 * 1e-3), "ms_per_step": ms_k20}
     del pw20, pw20_off, pub20
     eng.ed448_sign_dev(pw, pw_off, msg, msg_off, 512, h, z)  # h, z back to the 256-byte messages for what follows
 
-    # "next" rows N2 / N3: sponge AE over the cfg-2 shape (2^16 x 4 KB: two 4 KB KMAC passes per message,
-    # one absorbing, one squeezing into the XOR) and ECDHIES over 2^17 x 256 B, device-resident
+    # ---- "next" rows N2 / N3: sponge AE over the cfg-2 shape (2^16 x 4 KB: the tag pass and the keystream pass
+    # of the seal are one launch) and ECDHIES over 2^17 x 256 B, device-resident ------------------------------------
+    from oracle import ref_sha3
+
     nonces = rnd(n2 * 512)
     pw2 = rnd(n2 * 32)
     pw2_off = torch.arange(n2 + 1, dtype=torch.int64, device=dev) * 32
@@ -672,12 +852,21 @@ def extras(eng, dev, peaks, world, dist, rank):
     ms_e = timed(lambda: eng.sponge_encrypt_dev(pw2, pw2_off, n2 * 32, nonces, 512, data, m_off, 512, ct, tag), 5)
     ms_d = timed(lambda: eng.sponge_decrypt_dev(pw2, pw2_off, n2 * 32, nonces, 512, ct, m_off, tag, 512, pt, ok2), 5)
     assert bool(ok2.all().item()) and bool(torch.equal(pt, data)), "sponge AE round trip failed"
+    for i in idx2[:4]:  # the Python restatement of sha3/encryptable.rs:29-45 (slow: a handful of messages)
+        i = int(i)
+        c_ref, t_ref = ref_sha3.sha3_encrypt(data[i * mlen:(i + 1) * mlen].cpu().numpy().tobytes(), pw2[i * 32:(i + 1) * 32].cpu().numpy().tobytes(),
+                                             512, nonces[i * 512:(i + 1) * 512].cpu().numpy().tobytes())
+        assert ct[i * mlen:(i + 1) * mlen].cpu().numpy().tobytes() == c_ref and tag[i * 64:(i + 1) * 64].cpu().numpy().tobytes() == t_ref, \
+            "sha3_encrypt != oracle"
     ae_perms = 6 + 32 + 32  # key derivation (z || pw: 5 key blocks + 1) + tag pass + keystream (2 absorb + 30 squeeze); prefix cached
     out["sha3_encrypt_2^16x4KB"] = {
         "encrypt_GBps": world * n2 * mlen / (ms_e * 1e-3) / 1e9, "decrypt_GBps": world * n2 * mlen / (ms_d * 1e-3) / 1e9,
         "ms_encrypt": ms_e, "ms_decrypt": ms_d,
-        "frac_int_alu_encrypt": n2 * ae_perms * OPS_PER_PERM / (ms_e * 1e-3) / peaks["lop3"], "perms_per_msg": ae_perms}
+        "frac_int_alu_encrypt": n2 * ae_perms * OPS_PER_PERM / (ms_e * 1e-3) / peaks["lop3"],
+        "frac_int_alu_decrypt": n2 * ae_perms * OPS_PER_PERM / (ms_d * 1e-3) / peaks["lop3"], "perms_per_msg": ae_perms}
     del ct, pt, nonces
+
+    from oracle import ref_ed448
 
     n5 = 1 << 17
     k_rand = rnd(n5 * 56)
@@ -690,32 +879,28 @@ def extras(eng, dev, peaks, world, dist, rank):
     ms_e = timed(lambda: eng.ed448_key_encrypt_dev(pub, k_rand, m5, m5_off, 512, ct5, tag5, zpt), 2, 1)
     ms_d = timed(lambda: eng.ed448_key_decrypt_dev(pw, pw_off[: n5 + 1], zpt, ct5, m5_off, tag5, 512, pt5, ok5), 2, 1)
     assert bool(ok5.all().item()) and bool(torch.equal(pt5, m5)), "ECDHIES round trip failed"
+    for i in (0, n5 - 1):  # Python big-integer restatement of ecc/encryptable.rs:34-50
+        c_ref, t_ref, z_ref = ref_ed448.key_encrypt(ref_ed448.point_from_bytes(pub[i * 112:(i + 1) * 112].cpu().numpy().tobytes()),
+                                                    m5[i * 256:(i + 1) * 256].cpu().numpy().tobytes(), 512,
+                                                    k_rand[i * 56:(i + 1) * 56].cpu().numpy().tobytes())
+        assert ct5[i * 256:(i + 1) * 256].cpu().numpy().tobytes() == c_ref and tag5[i * 56:(i + 1) * 56].cpu().numpy().tobytes() == t_ref
+        assert zpt[i * 112:(i + 1) * 112].cpu().numpy().tobytes() == ref_ed448.point_to_bytes(z_ref), "key_encrypt != oracle"
     out["ed448_ecdhies_2^17x256B"] = {
         "key_encrypts_per_s": world * n5 / (ms_e * 1e-3), "key_decrypts_per_s": world * n5 / (ms_d * 1e-3),
         "ms_encrypt": ms_e, "ms_decrypt": ms_d,
         "note": "encrypt = 1 variable-base + 1 fixed-base scalar mult + 3 KMACs, decrypt = 1 variable-base + 4 KMACs"}
 
     # e2e for the Ed448 half of the metric: host buffers through capy_ed448_fixed_base_batch (H2D 56 B, D2H 112 B per item)
-    import time as _t
     n6 = 1 << 18
     h_sc = eng.pinned(n6 * 56)
     h_sc[:] = sc[: n6 * 56].cpu().numpy()
     h_pts = eng.pinned(n6 * 112).reshape(n6, 112)
-    eng.ed448_fixed_base(h_sc, out=h_pts)
-    if dist:
-        dist.barrier()
-    t0 = _t.perf_counter()
-    for _ in range(3):
-        eng.ed448_fixed_base(h_sc, out=h_pts)
-    dt = (_t.perf_counter() - t0) / 3
-    if dist:
-        t = torch.tensor([dt], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt = float(t.item())
+    dt = timed_host(lambda: eng.ed448_fixed_base(h_sc, out=h_pts), 3)
     assert h_pts[:1].tobytes() == pts[:112].cpu().numpy().tobytes()
     out["ed448_fixed_base_e2e_2^18"] = {"scalar_mults_per_s": world * n6 / dt, "ms_per_step": dt * 1e3,
                                         "h2d_bytes_per_step": n6 * 56, "d2h_bytes_per_step": n6 * 112,
                                         "api": "capy_ed448_fixed_base_batch (pinned host buffers from capy_host_alloc)"}
+    eng.set_plan_cache(False)
     return out
 
 

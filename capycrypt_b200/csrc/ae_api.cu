@@ -77,7 +77,9 @@ static KmacDevArgs ae_kmac_args(const AeCore& c, const uint8_t* key0, uint64_t n
   return a;
 }
 
-// t = KMACXOF(ka, m, tag, KA) ; c = KMACXOF(ke, "", |m|, KE) ^ m.  `ct` may alias `msgs` (in place).
+// t = KMACXOF(ka, m, tag, KA) ; c = KMACXOF(ke, "", |m|, KE) ^ m.  `ct` may alias `msgs` (in place): then the tag
+// pass has to finish before the keystream overwrites the message; otherwise the two passes are independent and go
+// out as ONE launch (launch_kmac_xof2: twice the warps, so the last wave of the grid is full).
 static int dev_ae_seal(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t st, const AeCore& c, const uint8_t* msgs,
                        const uint64_t* off, uint64_t n, uint8_t* ct, uint8_t* tag) {
   KmacDevArgs a = ae_kmac_args(c, c.keymat + c.klen, n, c.ka_custom);
@@ -85,12 +87,13 @@ static int dev_ae_seal(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t st, const AeCo
   a.off = off;
   a.out_bytes = a.out_stride = c.tag_bytes;
   a.out = tag;
-  int rc = launch_kmac_xof(ctx, dc, st, a);
-  if (rc) return rc;
   KmacDevArgs k = ae_kmac_args(c, c.keymat, n, c.ke_custom);
   k.out_off = off;
   k.out = ct;
   k.xor_in = msgs;
+  if (ct != msgs) return launch_kmac_xof2(ctx, dc, st, a, k);
+  int rc = launch_kmac_xof(ctx, dc, st, a);
+  if (rc) return rc;
   return launch_kmac_xof(ctx, dc, st, k);
 }
 
@@ -354,8 +357,8 @@ using namespace capy;
 
 #define CAPY_DEV_PROLOGUE                                                                   \
   if (!ctx || dev_index < 0 || dev_index >= (int)ctx->devs.size()) return CAPY_ERR_BAD_ARG; \
-  std::lock_guard<std::mutex> lk(ctx->mu); /* host-side state (scratch slots, tables) is shared */ \
   DeviceCtx& dc = ctx->devs[dev_index];                                                     \
+  std::lock_guard<std::mutex> lk(*dc.mu); /* host-side state of this device (scratch slots, tables) */ \
   DeviceGuard g(dc.dev);                                                                    \
   cudaStream_t st = (cudaStream_t)stream;
 
@@ -391,7 +394,6 @@ int capy_sponge_encrypt_batch(capy_ctx* ctx, int d_bits, int variant, const uint
   if (!valid_secparam(d_bits)) return CAPY_ERR_BAD_SECPARAM;
   if (variant != CAPY_AE_SHA3 && variant != CAPY_AE_KEM) return CAPY_ERR_BAD_ARG;
   if (n == 0) return CAPY_OK;
-  std::lock_guard<std::mutex> lk(ctx->mu);
   auto shards = split_items(msg_off, 0, 0, n, ctx->devs.size(), 2048);
   return for_each_device(ctx, shards, [&](DeviceCtx& dc, Range sh) -> int {
     cudaStream_t st = dc.streams[0];
@@ -427,7 +429,6 @@ int capy_sponge_decrypt_batch(capy_ctx* ctx, int d_bits, int variant, const uint
   if (!valid_secparam(d_bits)) return CAPY_ERR_BAD_SECPARAM;
   if (variant != CAPY_AE_SHA3 && variant != CAPY_AE_KEM) return CAPY_ERR_BAD_ARG;
   if (n == 0) return CAPY_OK;
-  std::lock_guard<std::mutex> lk(ctx->mu);
   auto shards = split_items(ct_off, 0, 0, n, ctx->devs.size(), 2048);
   return for_each_device(ctx, shards, [&](DeviceCtx& dc, Range sh) -> int {
     cudaStream_t st = dc.streams[0];
@@ -485,7 +486,6 @@ int capy_ed448_key_encrypt_batch(capy_ctx* ctx, int d_bits, const uint8_t* pub_x
   if (!ctx || (n && (!pub_xy112 || !k_rand56 || !msgs || !msg_off || !ct || !tag56 || !z_xy112))) return CAPY_ERR_BAD_ARG;
   if (!valid_secparam(d_bits)) return CAPY_ERR_BAD_SECPARAM;
   if (n == 0) return CAPY_OK;
-  std::lock_guard<std::mutex> lk(ctx->mu);
   std::vector<int> flags(ctx->devs.size(), 0);
   auto shards = split_items(msg_off, 0, 0, n, ctx->devs.size(), 16384);
   int rc = for_each_device(ctx, shards, [&](DeviceCtx& dc, Range sh) -> int {
@@ -513,7 +513,7 @@ int capy_ed448_key_encrypt_batch(capy_ctx* ctx, int d_bits, const uint8_t* pub_x
     if (rc) return rc;
     CAPY_CUDA(ctx, cudaMemcpyAsync(tag56 + 56 * sh.i0, d_tag, cnt * 56, cudaMemcpyDeviceToHost, st));
     CAPY_CUDA(ctx, cudaMemcpyAsync(z_xy112 + 112 * sh.i0, d_z, cnt * 112, cudaMemcpyDeviceToHost, st));
-    return read_flag(ctx, st, d_flag, &flags[&dc - &ctx->devs[0]]);
+    return read_flag(ctx, st, d_flag, &flags[dc.index]);
   });
   if (rc) return rc;
   for (int f : flags)
@@ -527,7 +527,6 @@ int capy_ed448_key_decrypt_batch(capy_ctx* ctx, int d_bits, const uint8_t* pws, 
   if (!ctx || (n && (!pws || !pw_off || !z_xy112 || !ct || !ct_off || !tag56 || !out || !ok))) return CAPY_ERR_BAD_ARG;
   if (!valid_secparam(d_bits)) return CAPY_ERR_BAD_SECPARAM;
   if (n == 0) return CAPY_OK;
-  std::lock_guard<std::mutex> lk(ctx->mu);
   std::vector<int> flags(ctx->devs.size(), 0);
   auto shards = split_items(ct_off, 0, 0, n, ctx->devs.size(), 16384);
   int rc = for_each_device(ctx, shards, [&](DeviceCtx& dc, Range sh) -> int {
@@ -556,7 +555,7 @@ int capy_ed448_key_decrypt_batch(capy_ctx* ctx, int d_bits, const uint8_t* pws, 
     rc = fetch_out(ctx, st, so, ct_off, sh.i0, sh.i1, out);
     if (rc) return rc;
     CAPY_CUDA(ctx, cudaMemcpyAsync(ok + sh.i0, d_ok, cnt, cudaMemcpyDeviceToHost, st));
-    return read_flag(ctx, st, d_flag, &flags[&dc - &ctx->devs[0]]);
+    return read_flag(ctx, st, d_flag, &flags[dc.index]);
   });
   if (rc) return rc;
   for (int f : flags)

@@ -8,6 +8,7 @@ namespace capy {
 
 int cuda_fail(capy_ctx* ctx, cudaError_t e, const char* what) {
   if (ctx) {
+    std::lock_guard<std::mutex> lk(ctx->err_mu);
     ctx->last_cuda_error = std::string(cudaGetErrorName(e)) + ": " + cudaGetErrorString(e) + " at " + what;
   }
   cudaGetLastError();  // clear sticky-less errors
@@ -39,7 +40,44 @@ void* scratch_get(DeviceCtx& dc, int slot, size_t bytes) {
   return s.p;
 }
 
-void ed448_tables_free(DeviceCtx& dc);  // ed448_api.cu
+void ed448_tables_free(DeviceCtx& dc);  // ed448_fixed.cu
+
+DeviceWorker::DeviceWorker(int dev) { th_ = std::thread([this, dev] { loop(dev); }); }
+DeviceWorker::~DeviceWorker() {
+  {
+    std::lock_guard<std::mutex> lk(m_);
+    stop_ = true;
+  }
+  cv_.notify_all();
+  if (th_.joinable()) th_.join();
+}
+void DeviceWorker::post(std::function<void()> f) {
+  {
+    std::lock_guard<std::mutex> lk(m_);
+    q_.push_back(std::move(f));
+  }
+  cv_.notify_one();
+}
+void DeviceWorker::loop(int dev) {
+  cudaSetDevice(dev);
+  for (;;) {
+    std::function<void()> f;
+    {
+      std::unique_lock<std::mutex> lk(m_);
+      cv_.wait(lk, [&] { return stop_ || !q_.empty(); });
+      if (q_.empty()) return;  // stop requested and nothing left to run
+      f = std::move(q_.front());
+      q_.pop_front();
+    }
+    f();
+  }
+}
+
+void plan_cache_clear(DeviceCtx& dc) {
+  for (PlanEntry& e : dc.plans)
+    if (e.owned_order) cudaFree(e.owned_order);  // cudaFree waits for work that still reads it
+  dc.plans.clear();
+}
 
 }  // namespace capy
 
@@ -87,6 +125,7 @@ int capy_gpu_init(const int* devices, int n_devices, capy_ctx** out_ctx) {
   for (size_t i = 0; i < devs.size(); i++) {
     DeviceCtx& dc = ctx->devs[i];
     dc.dev = devs[i];
+    dc.index = (int)i;
     DeviceGuard g(dc.dev);
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, dc.dev) != cudaSuccess) {
@@ -101,15 +140,19 @@ int capy_gpu_init(const int* devices, int n_devices, capy_ctx** out_ctx) {
       }
     }
   }
+  if (devs.size() > 1)
+    for (DeviceCtx& dc : ctx->devs) dc.worker.reset(new DeviceWorker(dc.dev));
   *out_ctx = ctx;
   return CAPY_OK;
 }
 
 void capy_gpu_destroy(capy_ctx* ctx) {
   if (!ctx) return;
+  for (DeviceCtx& dc : ctx->devs) dc.worker.reset();  // joins the worker threads
   for (DeviceCtx& dc : ctx->devs) {
     DeviceGuard g(dc.dev);
     cudaDeviceSynchronize();
+    plan_cache_clear(dc);
     for (int s = 0; s < kNumStreams; s++)
       if (dc.streams[s]) cudaStreamDestroy(dc.streams[s]);
     for (Scratch& sc : dc.scratch)
@@ -125,14 +168,26 @@ void capy_gpu_destroy(capy_ctx* ctx) {
 
 int capy_gpu_scrub(capy_ctx* ctx) {
   if (!ctx) return CAPY_ERR_BAD_ARG;
-  std::lock_guard<std::mutex> lk(ctx->mu);
   for (DeviceCtx& dc : ctx->devs) {
+    std::lock_guard<std::mutex> lk(*dc.mu);
     DeviceGuard g(dc.dev);
     CAPY_CUDA(ctx, cudaDeviceSynchronize());
     for (Scratch& sc : dc.scratch)
       if (sc.p) CAPY_CUDA(ctx, cudaMemset(sc.p, 0, sc.cap));
     CAPY_CUDA(ctx, cudaDeviceSynchronize());
   }
+  return CAPY_OK;
+}
+
+int capy_gpu_set_plan_cache(capy_ctx* ctx, int enable) {
+  if (!ctx) return CAPY_ERR_BAD_ARG;
+  ctx->plan_cache.store(enable ? 1 : 0);
+  if (!enable)
+    for (DeviceCtx& dc : ctx->devs) {
+      std::lock_guard<std::mutex> lk(*dc.mu);
+      DeviceGuard g(dc.dev);
+      plan_cache_clear(dc);
+    }
   return CAPY_OK;
 }
 
@@ -153,6 +208,52 @@ void* capy_host_alloc(size_t bytes) {
 
 void capy_host_free(void* p) {
   if (p) cudaFreeHost(p);
+}
+
+int capy_copy_probe(capy_ctx* ctx, int dev_index, const void* h_in, size_t in_bytes, void* h_out, size_t out_bytes, int reps,
+                    double* ms_per_rep) {
+  if (!ctx || dev_index < 0 || dev_index >= (int)ctx->devs.size() || !ms_per_rep || reps < 1 || (in_bytes && !h_in) ||
+      (out_bytes && !h_out))
+    return CAPY_ERR_BAD_ARG;
+  DeviceCtx& dc = ctx->devs[dev_index];
+  std::lock_guard<std::mutex> lk(*dc.mu);
+  DeviceGuard g(dc.dev);
+  // own buffers (not the scratch slots of the pipelines): plain copies, nothing else on the device
+  void *d_in = nullptr, *d_out = nullptr;
+  CAPY_CUDA(ctx, cudaMalloc(&d_in, in_bytes ? in_bytes : 16));
+  if (cudaMalloc(&d_out, out_bytes ? out_bytes : 16) != cudaSuccess) {
+    cudaFree(d_in);
+    return cuda_fail(ctx, cudaGetLastError(), "cudaMalloc(d_out)");
+  }
+  cudaEvent_t e0, e1, e2;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  cudaEventCreate(&e2);
+  cudaStream_t s0 = dc.streams[0], s1 = dc.streams[1];
+  int rc = CAPY_OK;
+  float ms = 0.f;
+  for (int pass = 0; pass < 2 && rc == CAPY_OK; pass++) {  // pass 0 = warm-up
+    const int n = pass == 0 ? 1 : reps;
+    cudaEventRecord(e0, s0);
+    cudaStreamWaitEvent(s1, e0, 0);
+    for (int r = 0; r < n; r++) {
+      if (in_bytes && cudaMemcpyAsync(d_in, h_in, in_bytes, cudaMemcpyHostToDevice, s0) != cudaSuccess) rc = CAPY_ERR_CUDA;
+      if (out_bytes && cudaMemcpyAsync(h_out, d_out, out_bytes, cudaMemcpyDeviceToHost, s1) != cudaSuccess) rc = CAPY_ERR_CUDA;
+    }
+    cudaEventRecord(e1, s1);
+    cudaStreamWaitEvent(s0, e1, 0);
+    cudaEventRecord(e2, s0);
+    if (cudaEventSynchronize(e2) != cudaSuccess) rc = CAPY_ERR_CUDA;
+    if (rc == CAPY_OK) cudaEventElapsedTime(&ms, e0, e2);
+  }
+  if (rc != CAPY_OK) cuda_fail(ctx, cudaGetLastError(), "capy_copy_probe");
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaEventDestroy(e2);
+  cudaFree(d_in);
+  cudaFree(d_out);
+  *ms_per_rep = (double)ms / reps;
+  return rc;
 }
 
 }  // extern "C"

@@ -324,8 +324,8 @@ using namespace capy;
 
 #define CAPY_DEV_PROLOGUE                                                                       \
   if (!ctx || dev_index < 0 || dev_index >= (int)ctx->devs.size()) return CAPY_ERR_BAD_ARG;     \
-  std::lock_guard<std::mutex> lk(ctx->mu); /* host-side state (scratch slots, tables) is shared */ \
   DeviceCtx& dc = ctx->devs[dev_index];                                                         \
+  std::lock_guard<std::mutex> lk(*dc.mu); /* host-side state of this device (scratch slots, tables) */ \
   DeviceGuard g(dc.dev);                                                                        \
   cudaStream_t st = (cudaStream_t)stream;
 
@@ -372,7 +372,6 @@ int capy_ed448_verify_batch_dev(capy_ctx* ctx, int dev_index, void* stream, int 
 int capy_ed448_fixed_base_batch(capy_ctx* ctx, const uint8_t* scalars_be56, uint64_t n, uint8_t* out_xy112) {
   if (!ctx || (n && (!scalars_be56 || !out_xy112))) return CAPY_ERR_BAD_ARG;
   if (n == 0) return CAPY_OK;
-  std::lock_guard<std::mutex> lk(ctx->mu);
   auto shards = split_items(nullptr, 1, 0, n, ctx->devs.size(), 0);
   return for_each_device(ctx, shards, [&](DeviceCtx& dc, Range sh) -> int {
     cudaStream_t st = dc.streams[0];
@@ -394,7 +393,6 @@ int capy_ed448_var_base_batch(capy_ctx* ctx, const uint8_t* scalars_be56, const 
                               uint8_t* out_xy112) {
   if (!ctx || (n && (!scalars_be56 || !points_xy112 || !out_xy112))) return CAPY_ERR_BAD_ARG;
   if (n == 0) return CAPY_OK;
-  std::lock_guard<std::mutex> lk(ctx->mu);
   std::vector<int> flags(ctx->devs.size(), 0);
   auto shards = split_items(nullptr, 1, 0, n, ctx->devs.size(), 0);
   int rc = for_each_device(ctx, shards, [&](DeviceCtx& dc, Range sh) -> int {
@@ -412,7 +410,7 @@ int capy_ed448_var_base_batch(capy_ctx* ctx, const uint8_t* scalars_be56, const 
     rc = dev_var_base(ctx, dc, st, d_sc, d_pt, cnt, d_out, d_flag);
     if (rc) return rc;
     CAPY_CUDA(ctx, cudaMemcpyAsync(out_xy112 + 112 * sh.i0, d_out, cnt * 112, cudaMemcpyDeviceToHost, st));
-    return read_flag(ctx, st, d_flag, &flags[&dc - &ctx->devs[0]]);
+    return read_flag(ctx, st, d_flag, &flags[dc.index]);
   });
   if (rc) return rc;
   for (int f : flags)
@@ -425,7 +423,6 @@ int capy_ed448_keygen_batch(capy_ctx* ctx, int d_bits, const uint8_t* pws, const
   if (!ctx || (n && (!pws || !pw_off || !out_xy112))) return CAPY_ERR_BAD_ARG;
   if (!valid_secparam(d_bits)) return CAPY_ERR_BAD_SECPARAM;
   if (n == 0) return CAPY_OK;
-  std::lock_guard<std::mutex> lk(ctx->mu);
   auto shards = split_items(nullptr, 1, 0, n, ctx->devs.size(), 0);
   return for_each_device(ctx, shards, [&](DeviceCtx& dc, Range sh) -> int {
     cudaStream_t st = dc.streams[0];
@@ -448,7 +445,6 @@ int capy_ed448_sign_batch(capy_ctx* ctx, int d_bits, const uint8_t* pws, const u
   if (!ctx || (n && (!pws || !pw_off || !msgs || !msg_off || !h56 || !z_be56))) return CAPY_ERR_BAD_ARG;
   if (!valid_secparam(d_bits)) return CAPY_ERR_BAD_SECPARAM;
   if (n == 0) return CAPY_OK;
-  std::lock_guard<std::mutex> lk(ctx->mu);
   auto shards = split_items(msg_off, 0, 0, n, ctx->devs.size(), 4096);
   return for_each_device(ctx, shards, [&](DeviceCtx& dc, Range sh) -> int {
     cudaStream_t st = dc.streams[0];
@@ -475,7 +471,6 @@ int capy_ed448_verify_batch(capy_ctx* ctx, int d_bits, const uint8_t* pub_xy112,
   if (!ctx || (n && (!pub_xy112 || !msgs || !msg_off || !h56 || !z_be56 || !ok))) return CAPY_ERR_BAD_ARG;
   if (!valid_secparam(d_bits)) return CAPY_ERR_BAD_SECPARAM;
   if (n == 0) return CAPY_OK;
-  std::lock_guard<std::mutex> lk(ctx->mu);
   std::vector<int> flags(ctx->devs.size(), 0);
   auto shards = split_items(msg_off, 0, 0, n, ctx->devs.size(), 4096);
   int rc = for_each_device(ctx, shards, [&](DeviceCtx& dc, Range sh) -> int {
@@ -498,7 +493,7 @@ int capy_ed448_verify_batch(capy_ctx* ctx, int d_bits, const uint8_t* pub_xy112,
     rc = dev_verify(ctx, dc, st, d_bits, d_pub, sm.d_base, sm.d_off, d_h, d_z, cnt, d_ok, d_flag);
     if (rc) return rc;
     CAPY_CUDA(ctx, cudaMemcpyAsync(ok + sh.i0, d_ok, cnt, cudaMemcpyDeviceToHost, st));
-    return read_flag(ctx, st, d_flag, &flags[&dc - &ctx->devs[0]]);
+    return read_flag(ctx, st, d_flag, &flags[dc.index]);
   });
   if (rc) return rc;
   for (int f : flags)
@@ -510,7 +505,6 @@ int capy_ed448_ecdh_batch(capy_ctx* ctx, const uint8_t* k_rand56, const uint8_t*
                           uint8_t* z_xy112) {
   if (!ctx || (n && (!k_rand56 || !pub_xy112 || !wx56))) return CAPY_ERR_BAD_ARG;
   if (n == 0) return CAPY_OK;
-  std::lock_guard<std::mutex> lk(ctx->mu);
   std::vector<int> flags(ctx->devs.size(), 0);
   auto shards = split_items(nullptr, 1, 0, n, ctx->devs.size(), 0);
   int rc = for_each_device(ctx, shards, [&](DeviceCtx& dc, Range sh) -> int {
@@ -548,7 +542,7 @@ int capy_ed448_ecdh_batch(capy_ctx* ctx, const uint8_t* k_rand56, const uint8_t*
       if (rc) return rc;
       CAPY_CUDA(ctx, cudaMemcpyAsync(z_xy112 + 112 * sh.i0, d_z, cnt * 112, cudaMemcpyDeviceToHost, st));
     }
-    return read_flag(ctx, st, d_flag, &flags[&dc - &ctx->devs[0]]);
+    return read_flag(ctx, st, d_flag, &flags[dc.index]);
   });
   if (rc) return rc;
   for (int f : flags)

@@ -74,10 +74,14 @@ static int ensure_tables(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t stream) {
   if (dc.ed && dc.ed->fb) return CAPY_OK;
   if (!dc.ed) dc.ed = new Ed448Tables();
   const size_t bytes = (size_t)FB_WINDOWS * FB_ENTRIES * FB_ENTRY_WORDS * sizeof(uint32_t);
-  CAPY_CUDA(ctx, cudaMalloc(&dc.ed->fb, bytes));
+  uint32_t* fb = nullptr;
+  CAPY_CUDA(ctx, cudaMalloc(&fb, bytes));
+  dc.ed->fb = fb;
   fb_table_kernel<<<(FB_WINDOWS + 31) / 32, 32, 0, stream>>>(dc.ed->fb);
   ctx->launches++;
   CAPY_CUDA(ctx, cudaGetLastError());
+  // once per device: later calls may launch on other (non-blocking) streams and must not see a half-built table
+  CAPY_CUDA(ctx, cudaStreamSynchronize(stream));
   return CAPY_OK;
 }
 

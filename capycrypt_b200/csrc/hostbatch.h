@@ -1,7 +1,8 @@
 // hostbatch.h -- host-buffer plumbing shared by the SHA3 and Ed448 entry points.
 #pragma once
 #include <algorithm>
-#include <thread>
+#include <condition_variable>
+#include <mutex>
 #include <vector>
 
 #include "internal.h"
@@ -47,21 +48,36 @@ inline std::vector<Range> split_items(const uint64_t* off, uint64_t fixed_len, u
   return r;
 }
 
+// Runs fn(device, shard) for every shard: inline on the caller's thread for a single shard, else on the devices'
+// persistent worker threads (DeviceWorker), each holding its device's lock for the duration of its closure.
 template <class F>
 inline int for_each_device(capy_ctx* ctx, const std::vector<Range>& shards, F&& fn) {
   if (shards.size() <= 1) {
     if (shards.empty()) return CAPY_OK;
-    DeviceGuard g(ctx->devs[0].dev);
-    return fn(ctx->devs[0], shards[0]);
+    DeviceCtx& dc = ctx->devs[0];
+    std::lock_guard<std::mutex> lk(*dc.mu);
+    DeviceGuard g(dc.dev);
+    return fn(dc, shards[0]);
   }
   std::vector<int> rcs(shards.size(), CAPY_OK);
-  std::vector<std::thread> th;
-  for (size_t k = 0; k < shards.size(); k++)
-    th.emplace_back([&, k] {
-      cudaSetDevice(ctx->devs[k].dev);
-      rcs[k] = fn(ctx->devs[k], shards[k]);
+  std::mutex m;
+  std::condition_variable cv;
+  size_t pending = shards.size();
+  for (size_t k = 0; k < shards.size(); k++) {
+    DeviceCtx& dc = ctx->devs[k];
+    dc.worker->post([&, k] {
+      {
+        std::lock_guard<std::mutex> lk(*ctx->devs[k].mu);
+        rcs[k] = fn(ctx->devs[k], shards[k]);
+      }
+      std::lock_guard<std::mutex> lk(m);
+      if (--pending == 0) cv.notify_one();
     });
-  for (auto& t : th) t.join();
+  }
+  {
+    std::unique_lock<std::mutex> lk(m);
+    cv.wait(lk, [&] { return pending == 0; });
+  }
   for (int rc : rcs)
     if (rc) return rc;
   return CAPY_OK;

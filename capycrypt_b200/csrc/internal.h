@@ -3,10 +3,15 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <condition_variable>
 #include <cstdint>
+#include <deque>
+#include <functional>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/capy_gpu.h"
@@ -27,26 +32,76 @@ struct PrefixState {
   uint8_t* d_prefix = nullptr;   // prefix bytes on the device
   uint32_t prefix_len = 0;
   uint32_t skip_blocks = 0;
+  uint64_t last_use = 0;         // LRU stamp (the customisation string is caller-controlled: the cache is bounded)
+};
+constexpr size_t kMaxPrefixEntries = 64;
+
+// How a ragged batch is launched (sha3_api.cu: plan_ragged).  `order` = work order (longest first) or nullptr.
+struct LaunchPlan {
+  const uint32_t* order = nullptr;
+  int warps_per_smsp = 0;   // 0 = unthrottled
+  uint64_t warp_items = 0;  // ranks [0, warp_items): one warp per item
+  uint64_t pair_items = 0;  // ranks [warp_items, warp_items + pair_items): two threads per item
+  uint32_t warp_cosched = 1;  // warp-tier chains per scheduler (1..4)
+};
+
+// Cached plan of a ragged batch, keyed by the caller's offsets array (capy_gpu_set_plan_cache): a repeated call with the
+// same (device pointer, n, unit) launches without touching the host.  A stale plan (the caller rewrote the offsets in
+// place) costs speed only: `order` stays a permutation of [0, n) and any item may run in any tier.
+struct PlanEntry {
+  const uint64_t* off = nullptr;
+  uint64_t n = 0;
+  uint32_t unit = 0;
+  bool allow_pair = true;
+  LaunchPlan plan;
+  uint32_t* owned_order = nullptr;
+  uint64_t last_use = 0;
+};
+constexpr size_t kMaxPlanEntries = 16;
+
+// persistent worker thread of one device of a multi-device ctx: host entry points post their per-device closure here
+// instead of spawning a std::thread per call
+class DeviceWorker {
+ public:
+  explicit DeviceWorker(int dev);
+  ~DeviceWorker();
+  void post(std::function<void()> f);
+
+ private:
+  void loop(int dev);
+  std::mutex m_;
+  std::condition_variable cv_;
+  std::deque<std::function<void()>> q_;
+  bool stop_ = false;
+  std::thread th_;
 };
 
 struct Ed448Tables;  // defined in ed448_api.cu
 
 struct DeviceCtx {
   int dev = 0;
+  int index = 0;  // position in capy_ctx::devs
   cudaStream_t streams[kNumStreams] = {};
   Scratch scratch[kNumScratch];
   std::map<std::string, PrefixState> prefix_cache;
+  std::vector<PlanEntry> plans;
+  uint64_t use_clock = 0;
   Ed448Tables* ed = nullptr;
   int sm_count = 0;
+  // host-side state of THIS device (scratch slots, caches, tables): one lock per device, so callers that use
+  // different devices of a ctx do not serialise
+  std::unique_ptr<std::mutex> mu{new std::mutex()};
+  std::unique_ptr<DeviceWorker> worker;  // only in a multi-device ctx
 };
 
 }  // namespace capy
 
 struct capy_ctx {
   std::vector<capy::DeviceCtx> devs;
-  std::mutex mu;
+  std::mutex err_mu;  // guards last_cuda_error only
   std::string last_cuda_error;
   std::atomic<uint64_t> launches{0};
+  std::atomic<int> plan_cache{0};
 };
 
 namespace capy {
@@ -98,5 +153,7 @@ struct KmacDevArgs {
   bool no_sort = false;  // keep the caller's order (skips the length bucketing and its tiny D2H sync)
 };
 int launch_kmac_xof(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t stream, const KmacDevArgs& a);
+// two passes over the same items (same d, same n) as one launch; the plan (work order) is taken from `a`
+int launch_kmac_xof2(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t stream, const KmacDevArgs& a, const KmacDevArgs& b);
 
 }  // namespace capy

@@ -247,26 +247,30 @@ __global__ void len_scatter_kernel(const uint64_t* __restrict__ off, uint64_t n,
   if (i < n) order[atomicAdd(&cursor[len_bin(off, i, stride_bytes)], 1u)] = (uint32_t)i;
 }
 
-struct LaunchPlan {
-  const uint32_t* order = nullptr;
-  int warps_per_smsp = 0;   // 0 = unthrottled
-  uint64_t warp_items = 0;  // ranks [0, warp_items): one warp per item
-  uint64_t pair_items = 0;  // ranks [warp_items, warp_items + pair_items): two threads per item
-};
-
 // Measured on B200 at one warp per scheduler, per permutation of ONE chain (csrc/keccak_pair_probe.cu in isolation,
 // tools/bench_tier_probe.py inside the sponge on 1 MiB SHA3-512 messages): one thread per state 4.55 / 4.6 us; a thread
-// pair 2.93 / 3.55 us; a whole warp per state 2.18 / 2.19 us.
+// pair 2.93 / 3.55 us; a whole warp per state 2.18 / 2.19 us.  A warp-tier chain issues only ~32 instructions per
+// ~180-clock round, so several of them can share a scheduler: with c chains per scheduler the 18 shuffles of a round
+// (one warp-wide shuffle per clock per SM) bound the round at 72 c clocks (tools/bench_tier_probe.py, CAPY_WARP_COSCHED).
 constexpr double kPairChainRatio = 3.55 / 4.6;
-constexpr double kWarpChainRatio = 2.2 / 4.6;
+constexpr int kMaxWarpCosched = 3;
+#ifndef CAPY_WARP_RATIO_2
+#define CAPY_WARP_RATIO_2 (2.35 / 4.6)
+#endif
+#ifndef CAPY_WARP_RATIO_3
+#define CAPY_WARP_RATIO_3 (2.9 / 4.6)
+#endif
+constexpr double kWarpChainRatio[kMaxWarpCosched + 1] = {0.0, 2.2 / 4.6, CAPY_WARP_RATIO_2, CAPY_WARP_RATIO_3};
 
 // Tiers of a chain-bound batch.  cum[k] = number of items in length bins > k (bin = whole blocks of the message).
-// Times are in units of one thread-per-state permutation; an SM hosts ONE block: 4 warp-tier, 64 pair-tier or 128
-// thread-tier items.  The smallest step time T is searched for which (a) every chain fits its tier, (b) the blocks of
-// the two fast tiers are all resident from the start and (c) the thread tier fits on the SMs that are left.
+// Times are in units of one thread-per-state permutation; an SM hosts ONE block: 4 c warp-tier (c chains per
+// scheduler), 64 pair-tier or 128 thread-tier items.  The smallest step time T is searched for which (a) every chain
+// fits its tier, (b) the blocks of the two fast tiers are all resident from the start and (c) the thread tier fits on
+// the SMs that are left; among the co-scheduling factors that reach it the smallest is taken.
 static void plan_tiers(const std::vector<uint32_t>& cum, uint64_t n, uint32_t max_blocks, double total_blocks, int sm_count,
-                       uint64_t* warp_items, uint64_t* pair_items) {
+                       uint64_t* warp_items, uint64_t* pair_items, uint32_t* warp_cosched, int force_c = 0) {
   *warp_items = *pair_items = 0;
+  *warp_cosched = 1;
   const size_t nb = cum.size();
   std::vector<double> work_above(nb);  // blocks in bins > k
   double acc = 0;
@@ -286,44 +290,87 @@ static void plan_tiers(const std::vector<uint32_t>& cum, uint64_t n, uint32_t ma
     *work = work_above[k];
   };
   const double l1 = (double)max_blocks;
-  for (double T = l1 * kWarpChainRatio; T < l1; T *= 1.04) {
+  for (double T = l1 * kWarpChainRatio[1]; T < l1; T *= 1.02) {
     uint64_t k_fast, k_w;
     double w_fast, w_w;
     longer_than(T, &k_fast, &w_fast);                 // must not run one thread per item
     longer_than(T / kPairChainRatio, &k_w, &w_w);     // must not even run as a pair
     if (k_w == 0 && T < l1 * kPairChainRatio) continue;  // (the pair tier alone cannot finish the longest item in T)
     const uint64_t k_p = k_fast - k_w;
-    const uint64_t blocks = (k_w + 3) / 4 + (k_p + 63) / 64;
-    if (blocks + 1 > (uint64_t)sm_count) continue;
-    // the thread-per-item tier gets the SMs the fast tiers leave (those stay busy for about T: their items are the
-    // longest); its items are dispatched longest first, so it needs its share of SMs from the start
-    if ((total_blocks - w_fast) / 128.0 > T * (double)((uint64_t)sm_count - blocks)) continue;
-    *warp_items = k_w;
-    *pair_items = k_p;
-    return;
+    const int c_lo = force_c >= 1 && force_c <= kMaxWarpCosched ? force_c : 1;
+    const int c_hi = force_c >= 1 && force_c <= kMaxWarpCosched ? force_c : kMaxWarpCosched;
+    for (int c = c_lo; c <= c_hi; c++) {
+      if (k_w && l1 * kWarpChainRatio[c] > T) break;  // the longest chain no longer fits at this sharing factor
+      const uint64_t blocks = (k_w + 4 * c - 1) / (4 * c) + (k_p + 63) / 64;
+      if (blocks + 1 > (uint64_t)sm_count) continue;
+      // the thread-per-item tier gets the SMs the fast tiers leave (those stay busy for about T: their items are the
+      // longest); its items are dispatched longest first, so it needs its share of SMs from the start
+      if ((total_blocks - w_fast) / 128.0 > T * (double)((uint64_t)sm_count - blocks)) continue;
+      *warp_items = k_w;
+      *pair_items = k_p;
+      *warp_cosched = (uint32_t)c;
+      return;
+    }
   }
 }
 
+void plan_cache_clear(DeviceCtx& dc);  // ctx.cu
+
 // builds the descending-length order for a ragged batch; decides the occupancy throttle and how many of the
-// longest items go to the two-threads-per-item kernel
+// longest items go to the warp-per-item and the two-threads-per-item tiers.
+// The histogram comes back to the host (two small D2H copies + stream synchronisations) because the grid shape
+// depends on it.  With the plan cache on (capy_gpu_set_plan_cache) the plan of an offsets array is kept, keyed by
+// (device pointer, n, unit): every later call with the same array launches without touching the host, so the
+// `_dev` entry points are fully asynchronous in steady state.
 static int plan_ragged(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t st, const uint64_t* d_off, uint64_t n,
-                       uint32_t stride_bytes, LaunchPlan* plan, bool allow_pair = true) {
+                       uint32_t stride_bytes, LaunchPlan* plan, bool allow_pair = true, int force_c = 0) {
   *plan = LaunchPlan();
   if (n < 1 || n > 0xffffffffull) return CAPY_OK;
+  const bool cached = ctx->plan_cache.load() != 0 && force_c == 0;
+  if (cached) {
+    for (PlanEntry& e : dc.plans)
+      if (e.off == d_off && e.n == n && e.unit == stride_bytes && e.allow_pair == allow_pair) {
+        e.last_use = ++dc.use_clock;
+        *plan = e.plan;
+        return CAPY_OK;
+      }
+  }
   int si = 0;  // scratch pair per internal stream (chunks on different streams overlap); callers' streams use pair 0
   for (int k = 0; k < kNumStreams; k++)
     if (dc.streams[k] == st) si = k;
   uint32_t* hist = (uint32_t*)scratch_get(dc, 18 + 2 * si, (size_t)kLenBins * 4 + 64);
-  uint32_t* order = (uint32_t*)scratch_get(dc, 19 + 2 * si, (size_t)n * 4);
-  if (!hist || !order) return CAPY_ERR_OOM;
+  uint32_t* order = nullptr;
+  uint32_t* owned = nullptr;
+  if (cached) {
+    if (cudaMalloc(&owned, (size_t)n * 4) != cudaSuccess) {
+      cudaGetLastError();
+      return CAPY_ERR_OOM;
+    }
+    order = owned;
+  } else {
+    order = (uint32_t*)scratch_get(dc, 19 + 2 * si, (size_t)n * 4);
+  }
+  if (!hist || !order) {
+    if (owned) cudaFree(owned);
+    return CAPY_ERR_OOM;
+  }
+  auto fail = [&](cudaError_t e, const char* what) {
+    if (owned) cudaFree(owned);
+    return cuda_fail(ctx, e, what);
+  };
+#define PLAN_CUDA(expr)                                  \
+  do {                                                   \
+    cudaError_t _e = (expr);                             \
+    if (_e != cudaSuccess) return fail(_e, #expr);       \
+  } while (0)
   uint32_t* summary = hist + kLenBins;
-  CAPY_CUDA(ctx, cudaMemsetAsync(hist, 0, (size_t)kLenBins * 4 + 64, st));
+  PLAN_CUDA(cudaMemsetAsync(hist, 0, (size_t)kLenBins * 4 + 64, st));
   len_hist_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_off, n, stride_bytes, hist);
   len_scan_kernel<<<1, 1024, 0, st>>>(hist, summary);
   ctx->launches += 2;
   uint32_t h_sum[4];
-  CAPY_CUDA(ctx, cudaMemcpyAsync(h_sum, summary, sizeof h_sum, cudaMemcpyDeviceToHost, st));
-  CAPY_CUDA(ctx, cudaStreamSynchronize(st));
+  PLAN_CUDA(cudaMemcpyAsync(h_sum, summary, sizeof h_sum, cudaMemcpyDeviceToHost, st));
+  PLAN_CUDA(cudaStreamSynchronize(st));
   const uint64_t total_blocks = (uint64_t)h_sum[0] | ((uint64_t)h_sum[1] << 32);
   const uint32_t max_blocks = h_sum[2] + 1, bins = h_sum[3];
   // time in units of one thread-per-state permutation on one scheduler: all work spread over every scheduler
@@ -332,41 +379,69 @@ static int plan_ragged(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t st, const uint
   // Chain-bound batch: the longest items go to the warp-per-item and the two-threads-per-item tiers
   if (allow_pair && max_blocks > 64 && (double)max_blocks > 1.05 * ideal) {
     std::vector<uint32_t> cum(kLenBins);  // after the scan hist[k] = number of items in bins > k
-    CAPY_CUDA(ctx, cudaMemcpyAsync(cum.data(), hist, (size_t)kLenBins * 4, cudaMemcpyDeviceToHost, st));
-    CAPY_CUDA(ctx, cudaStreamSynchronize(st));
-    plan_tiers(cum, n, max_blocks, (double)total_blocks, dc.sm_count, &plan->warp_items, &plan->pair_items);
+    PLAN_CUDA(cudaMemcpyAsync(cum.data(), hist, (size_t)kLenBins * 4, cudaMemcpyDeviceToHost, st));
+    PLAN_CUDA(cudaStreamSynchronize(st));
+    plan_tiers(cum, n, max_blocks, (double)total_blocks, dc.sm_count, &plan->warp_items, &plan->pair_items,
+               &plan->warp_cosched, force_c);
   }
-  if (bins <= 1) return CAPY_OK;  // uniform lengths: nothing to order
-  len_scatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_off, n, stride_bytes, hist, order);
-  ctx->launches++;
-  CAPY_CUDA(ctx, cudaGetLastError());
-  plan->order = order;
-  plan->warps_per_smsp = 0;
-  if ((double)max_blocks * 4.0 > 0.7 * ideal) {
-    plan->warps_per_smsp = 3;
-    if ((double)max_blocks * 3.0 > 0.7 * ideal) plan->warps_per_smsp = 2;
-    if ((double)max_blocks * 2.0 > 0.7 * ideal) plan->warps_per_smsp = 1;
+  if (bins > 1) {  // (uniform lengths: nothing to order)
+    len_scatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_off, n, stride_bytes, hist, order);
+    ctx->launches++;
+    PLAN_CUDA(cudaGetLastError());
+    plan->order = order;
+    plan->warps_per_smsp = 0;
+    if ((double)max_blocks * 4.0 > 0.7 * ideal) {
+      plan->warps_per_smsp = 3;
+      if ((double)max_blocks * 3.0 > 0.7 * ideal) plan->warps_per_smsp = 2;
+      if ((double)max_blocks * 2.0 > 0.7 * ideal) plan->warps_per_smsp = 1;
+    }
+  }
+#undef PLAN_CUDA
+  if (cached) {
+    if (!plan->order) {  // uniform batch: the entry records "nothing to do"
+      cudaFree(owned);
+      owned = nullptr;
+    }
+    if (dc.plans.size() >= kMaxPlanEntries) {  // evict the least recently used plan
+      size_t lru = 0;
+      for (size_t k = 1; k < dc.plans.size(); k++)
+        if (dc.plans[k].last_use < dc.plans[lru].last_use) lru = k;
+      if (dc.plans[lru].owned_order) cudaFree(dc.plans[lru].owned_order);  // waits for work that still reads it
+      dc.plans.erase(dc.plans.begin() + lru);
+    }
+    PlanEntry e;
+    e.off = d_off;
+    e.n = n;
+    e.unit = stride_bytes;
+    e.allow_pair = allow_pair;
+    e.plan = *plan;
+    e.owned_order = owned;
+    e.last_use = ++dc.use_clock;
+    dc.plans.push_back(e);
   }
   return CAPY_OK;
 }
 
 template <int LANES>
-static int launch_sponge_t(capy_ctx* ctx, cudaStream_t stream, SpongeJob J, unsigned block, int warps_per_smsp,
-                           uint64_t warp_items, uint64_t pair_items) {
+static int launch_sponge_t(capy_ctx* ctx, cudaStream_t stream, SpongeJob J, unsigned block, const LaunchPlan& plan) {
+  const uint64_t warp_items = plan.warp_items, pair_items = plan.pair_items;
   if (pair_items || warp_items) {
-    // chain-bound batch: warp blocks, then pair blocks, then thread-per-item blocks, one block per SM
-    const unsigned warp_blocks = grid_for(warp_items, 4);
+    // chain-bound batch: warp blocks, then pair blocks, then thread-per-item blocks, one block per SM.  A block has
+    // 128 c threads: the warp tier runs c chains per scheduler, the other tiers use the first four warps only.
+    const unsigned c = std::max(1u, std::min<unsigned>(plan.warp_cosched, kMaxWarpCosched));
+    const unsigned warp_blocks = grid_for(warp_items, 4 * c);
     const unsigned pair_blocks = grid_for(2 * pair_items, 128);
     const unsigned solo_blocks = grid_for(J.n - pair_items - warp_items, 128);
     J.warp_items = warp_items;
     J.first = warp_items + pair_items;
     CAPY_CUDA(ctx, cudaFuncSetAttribute(sponge_tiered_kernel<LANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-    sponge_tiered_kernel<LANES><<<warp_blocks + pair_blocks + solo_blocks, 128, 226 * 1024, stream>>>(J, warp_blocks, pair_blocks);
+    sponge_tiered_kernel<LANES><<<warp_blocks + pair_blocks + solo_blocks, 128 * c, 226 * 1024, stream>>>(J, warp_blocks, pair_blocks);
     ctx->launches++;
     CAPY_CUDA(ctx, cudaGetLastError());
     return CAPY_OK;
   }
   size_t smem = 0;
+  const int warps_per_smsp = plan.warps_per_smsp;
   if (warps_per_smsp >= 1 && warps_per_smsp <= 3) {
     // one 128-thread block = one warp per scheduler; W blocks per SM via the shared-memory footprint
     block = 128;
@@ -403,15 +478,13 @@ static int launch_sponge(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t stream, int 
                          const LaunchPlan& plan = LaunchPlan()) {
   if (J.n == 0) return CAPY_OK;
   const unsigned block = pick_block(J.n, dc.sm_count, 384);
-  const int w = plan.warps_per_smsp;
-  const uint64_t pi = plan.pair_items;
   switch (lanes) {
-    case 9: return launch_sponge_t<9>(ctx, stream, J, block, w, plan.warp_items, pi);
-    case 13: return launch_sponge_t<13>(ctx, stream, J, block, w, plan.warp_items, pi);
-    case 17: return launch_sponge_t<17>(ctx, stream, J, block, w, plan.warp_items, pi);
-    case 18: return launch_sponge_t<18>(ctx, stream, J, block, w, plan.warp_items, pi);
-    case 19: return launch_sponge_t<19>(ctx, stream, J, block, w, plan.warp_items, pi);
-    case 21: return launch_sponge_t<21>(ctx, stream, J, block, w, plan.warp_items, pi);
+    case 9: return launch_sponge_t<9>(ctx, stream, J, block, plan);
+    case 13: return launch_sponge_t<13>(ctx, stream, J, block, plan);
+    case 17: return launch_sponge_t<17>(ctx, stream, J, block, plan);
+    case 18: return launch_sponge_t<18>(ctx, stream, J, block, plan);
+    case 19: return launch_sponge_t<19>(ctx, stream, J, block, plan);
+    case 21: return launch_sponge_t<21>(ctx, stream, J, block, plan);
     default: return CAPY_ERR_BAD_ARG;
   }
 }
@@ -423,10 +496,22 @@ static SpongeJob empty_job() {
 }
 
 // ---- SHA3-d ------------------------------------------------------------------------------------
+// tail_readable: the 8-byte word that holds the last message byte of the LAST row may be read in full (the host entry
+// points stage into buffers with slack; a caller-owned device buffer may end with the last message byte)
 static int launch_sha3(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t stream, int d, const uint8_t* data, const uint64_t* off,
-                       uint64_t msg_len, uint64_t stride, uint64_t n, uint8_t* out, uint32_t flags = 0) {
+                       uint64_t msg_len, uint64_t stride, uint64_t n, uint8_t* out, uint32_t flags = 0,
+                       bool tail_readable = true) {
   if (!valid_secparam(d)) return CAPY_ERR_BAD_SECPARAM;
   if (n == 0) return CAPY_OK;
+  if (!off && !tail_readable && (msg_len & 7u) != 0 && n > 1 && (reinterpret_cast<uintptr_t>(data) & 7u) == 0 &&
+      (stride & 7u) == 0 && (reinterpret_cast<uintptr_t>(out) & 3u) == 0) {
+    // every row but the last has its tail word inside its own stride or the next row; the last row goes through the
+    // byte-granular kernel, which never reads past the message
+    int rc = launch_sha3(ctx, dc, stream, d, data, nullptr, msg_len, stride, n - 1, out, flags, true);
+    if (rc) return rc;
+    return launch_sha3(ctx, dc, stream, d, data + (n - 1) * stride, nullptr, msg_len, stride, 1, out + (n - 1) * (uint64_t)(d / 8),
+                       flags, false);
+  }
   const uint32_t rate = (1600 - sha3_capacity(d)) / 8;  // 144 / 136 / 104 / 72
   const int lanes = (int)rate / 8;
   if (!off && (reinterpret_cast<uintptr_t>(data) & 15u) == 0 && (reinterpret_cast<uintptr_t>(out) & 15u) == 0 &&
@@ -461,7 +546,9 @@ static int launch_sha3(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t stream, int d,
     CAPY_CUDA(ctx, cudaGetLastError());
     return CAPY_OK;
   }
-  if (!off && (reinterpret_cast<uintptr_t>(data) & 7u) == 0 && (stride & 7u) == 0) {
+  // the uniform kernel stores 4-byte granules (28- and 48-byte digests) and reads whole 8-byte words
+  if (!off && (reinterpret_cast<uintptr_t>(data) & 7u) == 0 && (stride & 7u) == 0 &&
+      (reinterpret_cast<uintptr_t>(out) & 3u) == 0 && (tail_readable || (msg_len & 7u) == 0)) {
     const uint32_t suffix = (msg_len % 136u == 135u) ? 0x86u : 0x06u;  // shake_functions.rs:25-29 (Q2)
     const unsigned block = 128, grid = grid_for(n, block);
     switch (lanes) {
@@ -488,7 +575,8 @@ static int launch_sha3(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t stream, int d,
   J.n = n;
   LaunchPlan plan;
   if (off && !(flags & CAPY_FLAG_NO_SORT)) {
-    int rc = plan_ragged(ctx, dc, stream, off, n, rate, &plan, !(flags & CAPY_FLAG_NO_PAIR));
+    int rc = plan_ragged(ctx, dc, stream, off, n, rate, &plan, !(flags & CAPY_FLAG_NO_PAIR),
+                         (int)((flags >> CAPY_FLAG_WARP_COSCHED_SHIFT) & 3u));
     if (rc) return rc;
   }
   J.order = plan.order;
@@ -522,8 +610,19 @@ static int get_prefix(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t stream, int d, 
   key.append(reinterpret_cast<const char*>(cs), cs_len);
   auto it = dc.prefix_cache.find(key);
   if (it != dc.prefix_cache.end()) {
+    it->second.last_use = ++dc.use_clock;
     *out = &it->second;
     return CAPY_OK;
+  }
+  // The customisation string is caller-controlled (compute_tagged_hash's S): bound the cache, least recently used out.
+  // cudaFree waits for work that still reads the evicted buffers.
+  if (dc.prefix_cache.size() >= kMaxPrefixEntries) {
+    auto lru = dc.prefix_cache.begin();
+    for (auto k = dc.prefix_cache.begin(); k != dc.prefix_cache.end(); ++k)
+      if (k->second.last_use < lru->second.last_use) lru = k;
+    if (lru->second.d_state) cudaFree(lru->second.d_state);
+    if (lru->second.d_prefix) cudaFree(lru->second.d_prefix);
+    dc.prefix_cache.erase(lru);
   }
   const uint32_t w = bytepad_value(d);
   std::string p;  // bytepad(encode_string(N) || encode_string(S), w)   shake_functions.rs:50-55
@@ -533,9 +632,19 @@ static int get_prefix(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t stream, int d, 
   p.append(w - p.size() % w, '\0');  // aux_functions.rs:14-16 (quirk Q3)
   PrefixState ps;
   ps.prefix_len = (uint32_t)p.size();
-  CAPY_CUDA(ctx, cudaMalloc(&ps.d_prefix, p.size()));
-  CAPY_CUDA(ctx, cudaMalloc(&ps.d_state, 25 * sizeof(uint64_t)));
-  CAPY_CUDA(ctx, cudaMemcpyAsync(ps.d_prefix, p.data(), p.size(), cudaMemcpyHostToDevice, stream));
+  auto fail = [&](cudaError_t e, const char* what) {  // nothing is cached on failure: free what was allocated
+    if (ps.d_prefix) cudaFree(ps.d_prefix);
+    if (ps.d_state) cudaFree(ps.d_state);
+    return cuda_fail(ctx, e, what);
+  };
+#define PREFIX_CUDA(expr)                          \
+  do {                                             \
+    cudaError_t _e = (expr);                       \
+    if (_e != cudaSuccess) return fail(_e, #expr); \
+  } while (0)
+  PREFIX_CUDA(cudaMalloc(&ps.d_prefix, p.size()));
+  PREFIX_CUDA(cudaMalloc(&ps.d_state, 25 * sizeof(uint64_t)));
+  PREFIX_CUDA(cudaMemcpyAsync(ps.d_prefix, p.data(), p.size(), cudaMemcpyHostToDevice, stream));
   const int lanes = (int)(w * 8 / 64);  // 21 / 21 / 19 / 17
   if (w % 8 == 0) {
     // the prefix is a whole number of blocks: fold it into a cached state once
@@ -546,12 +655,14 @@ static int get_prefix(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t stream, int d, 
       case 17: prefix_state_kernel<17><<<1, 32, 0, stream>>>(ps.d_prefix, ps.skip_blocks, ps.d_state); break;
     }
     ctx->launches++;
-    CAPY_CUDA(ctx, cudaGetLastError());
+    PREFIX_CUDA(cudaGetLastError());
   } else {
     ps.skip_blocks = 0;  // D224: w = 172 is not lane aligned (quirk Q7), blocks straddle the prefix end
   }
-  // the host string dies at return; make sure the copy has been consumed
-  CAPY_CUDA(ctx, cudaStreamSynchronize(stream));
+  // the host string dies at return, and later calls may use the entry from other streams: wait for the build
+  PREFIX_CUDA(cudaStreamSynchronize(stream));
+#undef PREFIX_CUDA
+  ps.last_use = ++dc.use_clock;
   auto ins = dc.prefix_cache.emplace(key, ps);
   *out = &ins.first->second;
   return CAPY_OK;
@@ -595,10 +706,7 @@ static int launch_cshake(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t stream, int 
   return launch_sponge(ctx, dc, stream, (int)(bytepad_value(d) * 8 / 64), J, plan);
 }
 
-int launch_kmac_xof(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t stream, const KmacDevArgs& a) {
-  if (!valid_secparam(a.d_bits)) return CAPY_ERR_BAD_SECPARAM;
-  if (a.n == 0) return CAPY_OK;
-  if (!a.out_off && a.out_bytes == 0) return CAPY_OK;
+static int build_kmac_job(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t stream, const KmacDevArgs& a, SpongeJob* out) {
   static const uint8_t kKmac[4] = {'K', 'M', 'A', 'C'};
   PrefixState* ps;
   int rc = get_prefix(ctx, dc, stream, a.d_bits, kKmac, 4, a.custom, a.custom_len, &ps);
@@ -621,17 +729,82 @@ int launch_kmac_xof(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t stream, const Kma
   J.out_bytes = a.out_bytes;
   J.xor_in = a.xor_in;
   J.n = a.n;
+  *out = J;
+  return CAPY_OK;
+}
+
+static int plan_kmac(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t stream, const KmacDevArgs& a, const SpongeJob& J, LaunchPlan* plan) {
+  *plan = LaunchPlan();
+  if (a.no_sort) return CAPY_OK;
+  if (a.off) return plan_ragged(ctx, dc, stream, a.off, a.n, J.rate & ~7u, plan);
+  // keystream shape (sha3/encryptable.rs:41): the work of an item is its squeeze length
+  if (a.out_off) return plan_ragged(ctx, dc, stream, a.out_off, a.n, 8u * J.sq_lanes, plan);
+  return CAPY_OK;
+}
+
+int launch_kmac_xof(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t stream, const KmacDevArgs& a) {
+  if (!valid_secparam(a.d_bits)) return CAPY_ERR_BAD_SECPARAM;
+  if (a.n == 0) return CAPY_OK;
+  if (!a.out_off && a.out_bytes == 0) return CAPY_OK;
+  SpongeJob J;
+  int rc = build_kmac_job(ctx, dc, stream, a, &J);
+  if (rc) return rc;
   LaunchPlan plan;
-  if (a.off && !a.no_sort) {
-    rc = plan_ragged(ctx, dc, stream, a.off, a.n, J.rate & ~7u, &plan);
-    if (rc) return rc;
-  } else if (!a.off && a.out_off && !a.no_sort) {
-    // keystream shape (sha3/encryptable.rs:41): the work of an item is its squeeze length
-    rc = plan_ragged(ctx, dc, stream, a.out_off, a.n, 8u * J.sq_lanes, &plan);
-    if (rc) return rc;
-  }
+  rc = plan_kmac(ctx, dc, stream, a, J, &plan);
+  if (rc) return rc;
   J.order = plan.order;
   return launch_sponge(ctx, dc, stream, (int)(bytepad_value(a.d_bits) * 8 / 64), J, plan);
+}
+
+// Two independent KMACXOF passes over the same items (same d, same n) as ONE launch: warps alternate between the two
+// jobs, so a batch whose single pass fills the schedulers unevenly (2^16 items = 3.46 warps per scheduler, the last
+// wave 15 % full) runs as 6.92 warps per scheduler.  The authenticated-encryption seal is such a pair: the tag pass
+// absorbs the message, the keystream pass squeezes into the XOR (sha3/encryptable.rs:36-42).  Both jobs follow the
+// plan of `a`.  Chain-bound batches (tiers) run the two passes one after the other.
+template <int LANES>
+static int launch_sponge2_t(capy_ctx* ctx, cudaStream_t stream, const SpongeJob& A, const SpongeJob& B, unsigned block,
+                            const LaunchPlan& plan) {
+  SpongeJob2 JJ;
+  JJ.j[0] = A;
+  JJ.j[1] = B;
+  size_t smem = 0;
+  if (plan.warps_per_smsp >= 1 && plan.warps_per_smsp <= 3) {
+    block = 128;
+    smem = (size_t)(227 * 1024 / plan.warps_per_smsp) - 1024;
+    CAPY_CUDA(ctx, cudaFuncSetAttribute(sponge_kernel2<LANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+  }
+  const uint64_t warps = 2 * ((A.n + 31) / 32);
+  sponge_kernel2<LANES><<<grid_for(warps * 32, block), block, smem, stream>>>(JJ);
+  ctx->launches++;
+  CAPY_CUDA(ctx, cudaGetLastError());
+  return CAPY_OK;
+}
+
+int launch_kmac_xof2(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t stream, const KmacDevArgs& a, const KmacDevArgs& b) {
+  if (!valid_secparam(a.d_bits) || a.d_bits != b.d_bits || a.n != b.n) return CAPY_ERR_BAD_ARG;
+  if (a.n == 0) return CAPY_OK;
+  SpongeJob JA, JB;
+  int rc = build_kmac_job(ctx, dc, stream, a, &JA);
+  if (rc) return rc;
+  rc = build_kmac_job(ctx, dc, stream, b, &JB);
+  if (rc) return rc;
+  LaunchPlan plan;
+  rc = plan_kmac(ctx, dc, stream, a, JA, &plan);
+  if (rc) return rc;
+  JA.order = JB.order = plan.order;
+  const int lanes = (int)(bytepad_value(a.d_bits) * 8 / 64);
+  if (plan.warp_items || plan.pair_items) {
+    rc = launch_sponge(ctx, dc, stream, lanes, JA, plan);
+    if (rc) return rc;
+    return launch_sponge(ctx, dc, stream, lanes, JB, plan);
+  }
+  const unsigned block = pick_block(2 * a.n, dc.sm_count, 384);
+  switch (lanes) {
+    case 17: return launch_sponge2_t<17>(ctx, stream, JA, JB, block, plan);
+    case 19: return launch_sponge2_t<19>(ctx, stream, JA, JB, block, plan);
+    case 21: return launch_sponge2_t<21>(ctx, stream, JA, JB, block, plan);
+    default: return CAPY_ERR_BAD_ARG;
+  }
 }
 
 }  // namespace capy
@@ -645,9 +818,15 @@ extern "C" {
 // =================================================================================================
 int capy_plan_tiers(const uint32_t* items_longer_than, uint32_t n_bins, uint64_t n, uint32_t max_blocks, uint64_t total_blocks,
                     int sm_count, uint64_t* warp_items, uint64_t* pair_items) {
-  if (!items_longer_than || !n_bins || !warp_items || !pair_items || sm_count < 2) return CAPY_ERR_BAD_ARG;
+  uint32_t c;
+  return capy_plan_tiers2(items_longer_than, n_bins, n, max_blocks, total_blocks, sm_count, warp_items, pair_items, &c);
+}
+
+int capy_plan_tiers2(const uint32_t* items_longer_than, uint32_t n_bins, uint64_t n, uint32_t max_blocks, uint64_t total_blocks,
+                     int sm_count, uint64_t* warp_items, uint64_t* pair_items, uint32_t* warp_cosched) {
+  if (!items_longer_than || !n_bins || !warp_items || !pair_items || !warp_cosched || sm_count < 2) return CAPY_ERR_BAD_ARG;
   std::vector<uint32_t> cum(items_longer_than, items_longer_than + n_bins);
-  plan_tiers(cum, n, max_blocks, (double)total_blocks, sm_count, warp_items, pair_items);
+  plan_tiers(cum, n, max_blocks, (double)total_blocks, sm_count, warp_items, pair_items, warp_cosched);
   return CAPY_OK;
 }
 
@@ -658,7 +837,7 @@ int capy_sha3_batch_dev(capy_ctx* ctx, int dev_index, void* stream, int d_bits, 
                         const uint64_t* d_off, uint64_t n, uint8_t* d_digests, uint32_t flags) {
   if (!ctx || dev_index < 0 || dev_index >= (int)ctx->devs.size() || (n && (!d_data || !d_off || !d_digests)))
     return CAPY_ERR_BAD_ARG;
-  std::lock_guard<std::mutex> lk(ctx->mu);  // host-side state (scratch slots, prefix cache) is shared
+  std::lock_guard<std::mutex> lk(*ctx->devs[dev_index].mu);  // host-side state of this device (scratch slots, caches)
   DeviceGuard g(ctx->devs[dev_index].dev);
   return launch_sha3(ctx, ctx->devs[dev_index], (cudaStream_t)stream, d_bits, d_data, d_off, 0, 0, n, d_digests, flags);
 }
@@ -667,9 +846,10 @@ int capy_sha3_batch_fixed_dev(capy_ctx* ctx, int dev_index, void* stream, int d_
                               uint64_t msg_len, uint64_t stride, uint64_t n, uint8_t* d_digests, uint32_t) {
   if (!ctx || dev_index < 0 || dev_index >= (int)ctx->devs.size() || (n && (!d_data || !d_digests)) || stride < msg_len)
     return CAPY_ERR_BAD_ARG;
-  std::lock_guard<std::mutex> lk(ctx->mu);  // host-side state (scratch slots, prefix cache) is shared
+  std::lock_guard<std::mutex> lk(*ctx->devs[dev_index].mu);  // host-side state of this device (scratch slots, caches)
   DeviceGuard g(ctx->devs[dev_index].dev);
-  return launch_sha3(ctx, ctx->devs[dev_index], (cudaStream_t)stream, d_bits, d_data, nullptr, msg_len, stride, n, d_digests);
+  return launch_sha3(ctx, ctx->devs[dev_index], (cudaStream_t)stream, d_bits, d_data, nullptr, msg_len, stride, n, d_digests, 0,
+                     /*tail_readable=*/false);
 }
 
 int capy_sha3_batch(capy_ctx* ctx, int d_bits, const uint8_t* data, const uint64_t* off, uint64_t n, uint8_t* digests,
@@ -677,7 +857,6 @@ int capy_sha3_batch(capy_ctx* ctx, int d_bits, const uint8_t* data, const uint64
   if (!ctx || (n && (!data || !off || !digests))) return CAPY_ERR_BAD_ARG;
   if (!valid_secparam(d_bits)) return CAPY_ERR_BAD_SECPARAM;
   if (n == 0) return CAPY_OK;
-  std::lock_guard<std::mutex> lk(ctx->mu);
   const size_t ob = (size_t)d_bits / 8;
   auto shards = split_items(off, 0, 0, n, ctx->devs.size(), 200);
   return for_each_device(ctx, shards, [&](DeviceCtx& dc, Range sh) -> int {
@@ -707,7 +886,6 @@ int capy_sha3_batch_fixed(capy_ctx* ctx, int d_bits, const uint8_t* data, uint64
   if (!ctx || (n && (!data || !digests)) || stride < msg_len) return CAPY_ERR_BAD_ARG;
   if (!valid_secparam(d_bits)) return CAPY_ERR_BAD_SECPARAM;
   if (n == 0) return CAPY_OK;
-  std::lock_guard<std::mutex> lk(ctx->mu);
   const size_t ob = (size_t)d_bits / 8;
   // the uniform kernel wants 8-byte aligned rows; the copy lands on a 256-byte aligned buffer, so
   // only the stride matters
@@ -743,7 +921,7 @@ int capy_cshake_batch_dev(capy_ctx* ctx, int dev_index, void* stream, int d_bits
   if (!ctx || dev_index < 0 || dev_index >= (int)ctx->devs.size() || (n && (!d_data || !d_off || !d_out)) ||
       (fn_len && !fn_name) || (custom_len && !custom))
     return CAPY_ERR_BAD_ARG;
-  std::lock_guard<std::mutex> lk(ctx->mu);  // host-side state (scratch slots, prefix cache) is shared
+  std::lock_guard<std::mutex> lk(*ctx->devs[dev_index].mu);  // host-side state of this device (scratch slots, caches)
   DeviceCtx& dc = ctx->devs[dev_index];
   DeviceGuard g(dc.dev);
   return launch_cshake(ctx, dc, (cudaStream_t)stream, d_bits, d_data, d_off, n, fn_name, fn_len, custom, custom_len,
@@ -757,7 +935,6 @@ int capy_cshake_batch(capy_ctx* ctx, int d_bits, const uint8_t* data, const uint
   if (!valid_secparam(d_bits)) return CAPY_ERR_BAD_SECPARAM;
   const size_t ob = (size_t)(out_bits / 8);
   if (n == 0 || ob == 0) return CAPY_OK;
-  std::lock_guard<std::mutex> lk(ctx->mu);
   auto shards = split_items(off, 0, 0, n, ctx->devs.size(), 200 + ob);
   return for_each_device(ctx, shards, [&](DeviceCtx& dc, Range sh) -> int {
     auto chunks = split_items(off, 0, sh.i0, sh.i1,
@@ -791,7 +968,7 @@ int capy_kmac_xof_batch_dev(capy_ctx* ctx, int dev_index, void* stream, int d_bi
   if (!ctx || dev_index < 0 || dev_index >= (int)ctx->devs.size() ||
       (n && (!d_keys || !d_key_off || !d_data || !d_off || !d_out)) || (custom_len && !custom))
     return CAPY_ERR_BAD_ARG;
-  std::lock_guard<std::mutex> lk(ctx->mu);  // host-side state (scratch slots, prefix cache) is shared
+  std::lock_guard<std::mutex> lk(*ctx->devs[dev_index].mu);  // host-side state of this device (scratch slots, caches)
   DeviceCtx& dc = ctx->devs[dev_index];
   DeviceGuard g(dc.dev);
   KmacDevArgs a{};
@@ -816,7 +993,7 @@ int capy_kmac_xof_batch_fixed_dev(capy_ctx* ctx, int dev_index, void* stream, in
   if (!ctx || dev_index < 0 || dev_index >= (int)ctx->devs.size() || (n && (!d_keys || !d_out)) ||
       (n && msg_len && !d_data) || (custom_len && !custom) || key_stride < key_len || msg_stride < msg_len)
     return CAPY_ERR_BAD_ARG;
-  std::lock_guard<std::mutex> lk(ctx->mu);  // host-side state (scratch slots, prefix cache) is shared
+  std::lock_guard<std::mutex> lk(*ctx->devs[dev_index].mu);  // host-side state of this device (scratch slots, caches)
   DeviceCtx& dc = ctx->devs[dev_index];
   DeviceGuard g(dc.dev);
   KmacDevArgs a{};
@@ -842,7 +1019,6 @@ int capy_kmac_xof_batch(capy_ctx* ctx, int d_bits, const uint8_t* keys, const ui
   if (!valid_secparam(d_bits)) return CAPY_ERR_BAD_SECPARAM;
   const size_t ob = (size_t)(out_bits / 8);
   if (n == 0 || (!out_off && ob == 0)) return CAPY_OK;
-  std::lock_guard<std::mutex> lk(ctx->mu);
   auto out_begin = [&](uint64_t i) -> uint64_t { return out_off ? out_off[i] : i * ob; };
   auto shards = split_items(off, 0, 0, n, ctx->devs.size(), 400 + ob);
   return for_each_device(ctx, shards, [&](DeviceCtx& dc, Range sh) -> int {
@@ -901,7 +1077,7 @@ int capy_fips_shake_batch_dev(capy_ctx* ctx, int dev_index, void* stream, int sh
       (shake_bits != 128 && shake_bits != 256))
     return CAPY_ERR_BAD_ARG;
   if (n == 0 || out_bytes == 0) return CAPY_OK;
-  std::lock_guard<std::mutex> lk(ctx->mu);  // host-side state (scratch slots, prefix cache) is shared
+  std::lock_guard<std::mutex> lk(*ctx->devs[dev_index].mu);  // host-side state of this device (scratch slots, caches)
   DeviceGuard g(ctx->devs[dev_index].dev);
   SpongeJob J = empty_job();
   J.data = d_data;

@@ -577,6 +577,20 @@ __global__ void __launch_bounds__(128, CAPY_SPONGE_MINB) sponge_kernel(const Spo
   sponge_item<LANES>(J, sponge_rank_item(J, r));
 }
 
+// Two jobs over the same number of items in one launch: warps alternate between job 0 and job 1 (warp w works on
+// job w & 1, ranks 32 (w >> 1) ..), so neither job waits for the other's blocks and no warp mixes the two code paths.
+struct SpongeJob2 {
+  SpongeJob j[2];
+};
+template <int LANES>
+__global__ void __launch_bounds__(128, CAPY_SPONGE_MINB) sponge_kernel2(const __grid_constant__ SpongeJob2 JJ) {
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const SpongeJob& J = JJ.j[(t >> 5) & 1u];
+  const uint64_t r = ((t >> 6) << 5) | (t & 31u);
+  if (r >= J.n) return;
+  sponge_item<LANES>(J, sponge_rank_item(J, r));
+}
+
 // Chain-bound ragged batch in ONE launch, three tiers by rank in the length-sorted order:
 //   blocks [0, warp_blocks)                        one WARP per item   ranks [0, J.warp_items)        4 items per block
 //   blocks [warp_blocks, warp_blocks + pair_blocks) two threads per item ranks [J.warp_items, J.first)  64 items per block
@@ -596,21 +610,26 @@ __device__ __noinline__ void sponge_item_pair_ool(const SpongeJob& J, uint64_t i
 }
 
 template <int LANES>
-__global__ void __launch_bounds__(128, 1) sponge_tiered_kernel(const SpongeJob J, uint32_t warp_blocks, uint32_t pair_blocks) {
-  // __launch_bounds__(128, 1): with the default bound ptxas held the kernel at 128 registers and, once the unrolled
+__global__ void __launch_bounds__(384, 1) sponge_tiered_kernel(const SpongeJob J, uint32_t warp_blocks, uint32_t pair_blocks) {
+  // __launch_bounds__(.., 1): with the default bound ptxas held the kernel at 128 registers and, once the unrolled
   // warp-tier permutation was part of it, scheduled the (instruction-for-instruction identical) round loop of the
   // thread tier differently: 5.4 instead of 4.6 us per permutation at one warp per scheduler.
-  if (blockIdx.x >= warp_blocks + pair_blocks) {
-    const uint64_t r = J.first + (uint64_t)(blockIdx.x - warp_blocks - pair_blocks) * blockDim.x + threadIdx.x;
-    if (r >= J.n) return;
-    sponge_item_solo_ool<LANES>(J, sponge_rank_item(J, r));
-  } else if (blockIdx.x >= warp_blocks) {
-    const uint64_t t = (uint64_t)(blockIdx.x - warp_blocks) * blockDim.x + threadIdx.x;
-    const uint64_t r = J.warp_items + (t >> 1);
-    const bool valid = r < J.first;  // idle pairs of the last warp still take part in the shuffles
-    sponge_item_pair_ool<LANES>(J, valid ? sponge_rank_item(J, r) : 0, valid, (uint32_t)(t & 1));
+  // blockDim.x = 128 c: the warp tier runs c chains per scheduler (a warp-tier chain issues ~32 instructions per
+  // ~180-clock round), the pair and thread tiers want a scheduler per warp and use the first four warps only.
+  if (blockIdx.x >= warp_blocks) {
+    if (threadIdx.x >= 128) return;
+    if (blockIdx.x >= warp_blocks + pair_blocks) {
+      const uint64_t r = J.first + (uint64_t)(blockIdx.x - warp_blocks - pair_blocks) * 128 + threadIdx.x;
+      if (r >= J.n) return;
+      sponge_item_solo_ool<LANES>(J, sponge_rank_item(J, r));
+    } else {
+      const uint64_t t = (uint64_t)(blockIdx.x - warp_blocks) * 128 + threadIdx.x;
+      const uint64_t r = J.warp_items + (t >> 1);
+      const bool valid = r < J.first;  // idle pairs of the last warp still take part in the shuffles
+      sponge_item_pair_ool<LANES>(J, valid ? sponge_rank_item(J, r) : 0, valid, (uint32_t)(t & 1));
+    }
   } else {
-    const uint64_t r = (uint64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+    const uint64_t r = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (r >= J.warp_items) return;  // whole warps leave together
     sponge_item_warp<LANES>(J, sponge_rank_item(J, r));
   }

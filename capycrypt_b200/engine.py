@@ -96,6 +96,17 @@ class Engine:
         """zero every device scratch buffer of the ctx (intermediate secrets of the pipelines live there)"""
         self._check(self.lib.capy_gpu_scrub(self._ctx))
 
+    def copy_probe(self, h_in: np.ndarray, h_out: np.ndarray, reps: int = 10, dev_index: int = 0) -> float:
+        """capy_copy_probe: ms per repetition of (H2D of h_in) overlapped with (D2H into h_out), no kernel"""
+        ms = C.c_double(0.0)
+        self._check(self.lib.capy_copy_probe(self._ctx, dev_index, _hp(h_in), h_in.size, _hp(h_out), h_out.size, reps,
+                                             C.byref(ms)))
+        return float(ms.value)
+
+    def set_plan_cache(self, enable: bool = True):
+        """capy_gpu_set_plan_cache: ragged calls that pass the same offsets array again launch without a host round trip"""
+        self._check(self.lib.capy_gpu_set_plan_cache(self._ctx, 1 if enable else 0))
+
     # ---- plumbing ----
     def _check(self, rc: int, allow=()):
         if rc != B.OK and rc not in allow:

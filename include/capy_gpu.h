@@ -57,6 +57,9 @@ extern "C" {
 /* chain-bound ragged batches run their longest messages with two threads per message (the chain of one message
  * advances faster); this flag keeps one thread per message everywhere (A/B measurements) */
 #define CAPY_FLAG_NO_PAIR 2u
+/* diagnostics: force the number of warp-tier chains that share a warp scheduler (1..3) in a chain-bound ragged batch
+ * instead of letting the planner choose: flags |= c << CAPY_FLAG_WARP_COSCHED_SHIFT */
+#define CAPY_FLAG_WARP_COSCHED_SHIFT 8
 
 typedef struct capy_ctx capy_ctx;
 
@@ -76,8 +79,23 @@ int capy_version(void);
 /* pinned host memory helpers (optional; faster H2D/D2H for the host entry points) */
 void* capy_host_alloc(size_t bytes);
 void capy_host_free(void* p);
+/* Measurement aid: the ceiling of the host <-> device link for this process.  Per repetition one plain cudaMemcpyAsync
+ * of in_bytes host -> device and one of out_bytes device -> host, on two streams so the two directions overlap, no
+ * kernel; ms_per_rep is device-timed (events).  Buffers from capy_host_alloc give the pinned-memory figure.  bench.py
+ * reports the engine's end-to-end throughput as a fraction of this. */
+int capy_copy_probe(capy_ctx* ctx, int dev_index, const void* h_in, size_t in_bytes, void* h_out, size_t out_bytes,
+                    int reps, double* ms_per_rep);
 /* number of kernels this ctx has launched so far (bench.py's gpu_launches evidence) */
 uint64_t capy_launch_count(const capy_ctx* ctx);
+/* Plan cache for ragged batches.  A ragged sponge call orders its items longest-first and, for chain-bound batches,
+ * splits them into tiers; the shape of that launch depends on the length histogram, which the host reads back (two
+ * small D2H copies + stream synchronisations).  With the cache enabled the plan of an offsets array is kept, keyed by
+ * (device pointer, n, unit), and every later call that passes the same array -- _dev entry points: the caller's device
+ * array; cSHAKE / KMAC / AE alike -- launches without touching the host: the call is asynchronous on the caller's
+ * stream.  Contract: an offsets array passed again under the same address has not changed.  A stale plan costs speed,
+ * never correctness (the work order stays a permutation of the items and any item may run in any tier).  At most 16
+ * plans per device (least recently used evicted); enable = 0 drops them.  Off by default. */
+int capy_gpu_set_plan_cache(capy_ctx* ctx, int enable);
 
 /* ---- diagnostics: the host-side launch planner of chain-bound ragged sponge batches (no GPU needed) ------- */
 /* items_longer_than[k] = number of items whose message has MORE than k whole rate blocks (k < n_bins), n items,
@@ -85,6 +103,11 @@ uint64_t capy_launch_count(const capy_ctx* ctx);
  * warp per item and how many of the next with two threads per item (DESIGN.md "chain-bound batches"). */
 int capy_plan_tiers(const uint32_t* items_longer_than, uint32_t n_bins, uint64_t n, uint32_t max_blocks,
                     uint64_t total_blocks, int sm_count, uint64_t* warp_items, uint64_t* pair_items);
+/* same, and how many warp-tier chains share a warp scheduler (1..3): a warp-tier chain uses a fraction of its
+ * scheduler's issue slots, so a batch with more long messages than schedulers co-schedules them */
+int capy_plan_tiers2(const uint32_t* items_longer_than, uint32_t n_bins, uint64_t n, uint32_t max_blocks,
+                     uint64_t total_blocks, int sm_count, uint64_t* warp_items, uint64_t* pair_items,
+                     uint32_t* warp_cosched);
 
 /* ---- SHA3-d : SpongeHashable::compute_sha3_hash (sha3/hashable.rs:19-21 -> shake,
  *      sha3/shake_functions.rs:24-32 -> sponge_absorb/squeeze, sha3/sponge.rs:10-34) ------- */

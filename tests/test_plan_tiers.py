@@ -1,8 +1,9 @@
 """CPU: the host-side launch planner of chain-bound sponge batches (csrc/sha3_api.cu plan_tiers, exported for tests as
 capy_plan_tiers).  No GPU needed: the planner is pure host logic over the length histogram.
 
-Model behind the expectations: one block per SM; a block carries 4 warp-tier, 64 pair-tier or 128
-thread-tier items; per permutation a thread-tier chain takes 1 unit, a pair 0.77, a warp 0.48."""
+Model behind the expectations: one block per SM; a block carries 4 c warp-tier (c = 1..3 chains per
+scheduler), 64 pair-tier or 128 thread-tier items; per permutation a thread-tier chain takes 1 unit, a pair 0.77, a
+warp 0.48 alone on its scheduler and more when it shares it."""
 import ctypes as C
 
 import numpy as np
@@ -18,15 +19,20 @@ def lib():
     return B.load()
 
 
-def plan(lib, lens_blocks, sm=148):
+def plan(lib, lens_blocks, sm=148, with_c=False):
     lens_blocks = np.asarray(lens_blocks, dtype=np.int64)
     bins = np.minimum(lens_blocks, NB - 1)
     hist = np.bincount(bins, minlength=NB)
     longer = (len(bins) - np.cumsum(hist)).astype(np.uint32)  # items in bins > k
-    w, p = C.c_uint64(), C.c_uint64()
-    rc = lib.capy_plan_tiers(longer.ctypes.data, NB, len(bins), int(bins.max()) + 1, int((bins + 1).sum()), sm,
-                             C.addressof(w), C.addressof(p))
+    w, p, c = C.c_uint64(), C.c_uint64(), C.c_uint32()
+    rc = lib.capy_plan_tiers2(longer.ctypes.data, NB, len(bins), int(bins.max()) + 1, int((bins + 1).sum()), sm,
+                              C.addressof(w), C.addressof(p), C.addressof(c))
     assert rc == 0
+    w2, p2 = C.c_uint64(), C.c_uint64()
+    assert lib.capy_plan_tiers(longer.ctypes.data, NB, len(bins), int(bins.max()) + 1, int((bins + 1).sum()), sm,
+                               C.addressof(w2), C.addressof(p2)) == 0 and (w2.value, p2.value) == (w.value, p.value)
+    if with_c:
+        return int(w.value), int(p.value), int(c.value)
     return int(w.value), int(p.value)
 
 
@@ -35,9 +41,12 @@ def test_single_long_message_gets_a_warp(lib):
     assert plan(lib, [14563] * 64) == (64, 0)    # 64 x 1 MiB: 16 blocks of 4 warps
 
 
-def test_many_equal_long_messages_prefer_the_pair_tier_when_warps_do_not_fit(lib):
-    w, p = plan(lib, [14563] * 1024)             # 256 warp blocks would not fit 148 SMs
-    assert w == 0 and p == 1024
+def test_long_messages_share_schedulers_before_they_fall_back_to_the_pair_tier(lib):
+    assert plan(lib, [14563] * 64, with_c=True) == (64, 0, 1)       # a scheduler each
+    assert plan(lib, [14563] * 1024, with_c=True) == (1024, 0, 2)   # 256 blocks of 4 do not fit 148 SMs, 128 blocks of 8 do
+    assert plan(lib, [14563] * 1600, with_c=True) == (1600, 0, 3)   # 134 blocks of 12
+    w, p = plan(lib, [14563] * 2400)             # 200 blocks of 12 would not fit: two threads per message
+    assert w == 0 and p == 2400
 
 
 def test_work_bound_batch_has_no_fast_tier(lib):
@@ -63,12 +72,16 @@ def test_mixed_batches_like_config_5(lib):
     w, p = plan(lib, _mixed(16 << 30))
     assert w == 0 and 500 <= p <= 3000
     # the 2 GiB shard of an 8-GPU run: chain-bound -> both fast tiers, all of their blocks resident at once
-    w, p = plan(lib, _mixed(2 << 30))
-    assert w > 0 and p > 0 and (w + 3) // 4 + (p + 63) // 64 < 148
+    w, p, c = plan(lib, _mixed(2 << 30), with_c=True)
+    assert w > 0 and p > 0 and 1 <= c <= 3 and (w + 4 * c - 1) // (4 * c) + (p + 63) // 64 < 148
     # every chain must fit the step the planner assumed: the first thread-tier item is shorter than the first pair item
     # times 0.77 / 1 and the first pair item shorter than the longest times 0.48 / 0.77
     lens = np.sort(_mixed(2 << 30))[::-1] + 1
     assert lens[w + p] <= lens[w] and lens[w] * 0.772 >= lens[0] * 0.478 * 0.99
+    # the shards of a 2- and a 4-GPU run hold more long messages than there are schedulers: they get a warp tier too
+    for total in (8 << 30, 4 << 30):
+        w, p, c = plan(lib, _mixed(total), with_c=True)
+        assert w > 0 and (w + 4 * c - 1) // (4 * c) + (p + 63) // 64 < 148, (total, w, p, c)
 
 
 def test_bad_arguments(lib):

@@ -33,3 +33,13 @@ for name, lens in cases:
     b, ob = run(lens, 512, 2, data)
     print(json.dumps({"case": name, "n": len(lens), "tiered_ms": round(a, 2), "one_thread_per_msg_ms": round(b, 2), "same": bool(torch.equal(oa, ob))}))
     del data
+# warp-tier chain speed when c chains share a scheduler (flags = c << CAPY_FLAG_WARP_COSCHED_SHIFT forces the planner's
+# co-scheduling factor): 74 SMs x 4 c messages of 1 MiB, and a full GPU (148 SMs) for c = 1..3 where the blocks fit
+for c in (1, 2, 3):
+    for sms in (74, 147):
+        lens = np.full(sms * 4 * c, 1 << 20, dtype=np.int64)
+        data = torch.empty(int(lens.sum()) + 16, dtype=torch.uint8, device=dev); data.random_(0, 256)
+        a, oa = run(lens, 512, c << 8, data, reps=1)
+        print(json.dumps({"case": f"warp tier, {c} chains per scheduler, {sms} SMs", "n": len(lens), "ms": round(a, 2),
+                          "us_per_perm": round(a * 1e3 / 14564, 3)}))
+        del data
