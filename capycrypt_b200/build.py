@@ -71,7 +71,7 @@ def build(force: bool = False, defines=(), verbose: bool = False, lib: str = LIB
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
     # standalone measurement tools: integer-pipe peaks (roofline denominators), Keccak unroll/block-size sweep,
     # chain speed of the split-lane / 25-thread permutations (profiles/r01*_keccak_*.jsonl)
-    for tool in ("peaks", "keccak_sweep", "keccak_pair_probe"):
+    for tool in ("peaks", "keccak_sweep", "keccak_pair_probe", "fe_mul_probe"):
         r = subprocess.run([NVCC, *BASE_FLAGS, os.path.join(CSRC, tool + ".cu"), "-o", os.path.join(LIBDIR, tool),
                             "-cudart", "static"], capture_output=True, text=True)
         if r.returncode != 0:

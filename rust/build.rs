@@ -13,9 +13,6 @@ fn main() {
         let mut cmd = Command::new(&nvcc);
         cmd.args(["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
                   "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-c"]);
-        if s == "ed448_var.cu" {
-            cmd.args(["-DCAPY_FE_OOL", "-DCAPY_VB_HOT_INLINE", "-DCAPY_VB_ADD_OOL", "-DCAPY_VB_SYNC", "-DCAPY_ED_MINBLOCKS=3"]);
-        }
         let status = cmd.arg(format!("gpu/csrc/{s}")).arg("-o").arg(&obj).status().expect("nvcc not found");
         assert!(status.success(), "nvcc failed on {s} (there is no CPU fallback)");
         objs.push(obj);

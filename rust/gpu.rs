@@ -2,12 +2,14 @@
 //!
 //! SOURCE-ONLY DELIVERABLE: this image has no rustc/cargo, so this file has not been compiled.  It is the
 //! binding a capyCRYPT maintainer adds as `src/gpu.rs` (+ `pub mod gpu;` in `src/lib.rs` and the `build.rs`
-//! next to this file).  Every `extern "C"` item mirrors one declaration of `include/capy_gpu.h`.
+//! next to this file).  The `extern "C"` block binds EVERY export of `include/capy_gpu.h`; it is generated from the
+//! header by `tools/gen_rust_extern.py` and `tests/test_rust_shim.py` checks names, arity and parameter types of the two
+//! against each other, so the block cannot drift although this file has never been through rustc.
 //!
 //! The existing API stays the contract: results land in the same `Message` fields the scalar
 //! traits fill (`SpongeHashable::compute_sha3_hash` -> `.digest`, `Signable::sign` -> `.sig`, `.d`).
 use crate::{ecc::keypair::KeyPair, ecc::signable::Signature, Message, OperationError, SecParam};
-use std::os::raw::{c_int, c_void};
+use std::os::raw::{c_char, c_int, c_void};
 use tiny_ed448_goldilocks::curve::{extended_edwards::ExtendedPoint, field::scalar::Scalar};
 
 #[repr(C)]
@@ -19,29 +21,92 @@ pub struct CapyCtx {
 extern "C" {
     fn capy_gpu_init(devices: *const c_int, n_devices: c_int, out_ctx: *mut *mut CapyCtx) -> c_int;
     fn capy_gpu_destroy(ctx: *mut CapyCtx);
-    fn capy_sha3_batch(ctx: *mut CapyCtx, d_bits: c_int, data: *const u8, off: *const u64, n: u64,
-                       digests: *mut u8, flags: u32) -> c_int;
-    fn capy_kmac_xof_batch(ctx: *mut CapyCtx, d_bits: c_int, keys: *const u8, key_off: *const u64,
-                           data: *const u8, off: *const u64, n: u64, custom: *const u8, custom_len: u32,
-                           out_bits: u64, out_off: *const u64, out: *mut u8) -> c_int;
+    fn capy_gpu_device_count(ctx: *const CapyCtx) -> c_int;
+    fn capy_gpu_scrub(ctx: *mut CapyCtx) -> c_int;
+    fn capy_strerror(status: c_int) -> *const c_char;
+    fn capy_last_cuda_error(ctx: *const CapyCtx) -> *const c_char;
+    fn capy_version() -> c_int;
+    fn capy_host_alloc(bytes: usize) -> *mut c_void;
+    fn capy_host_free(p: *mut c_void);
+    fn capy_copy_probe(ctx: *mut CapyCtx, dev_index: c_int, h_in: *const c_void, in_bytes: usize, h_out: *mut c_void,
+        out_bytes: usize, reps: c_int, ms_per_rep: *mut f64) -> c_int;
+    fn capy_launch_count(ctx: *const CapyCtx) -> u64;
+    fn capy_gpu_set_plan_cache(ctx: *mut CapyCtx, enable: c_int) -> c_int;
+    fn capy_plan_tiers(items_longer_than: *const u32, n_bins: u32, n: u64, max_blocks: u32, total_blocks: u64,
+        sm_count: c_int, warp_items: *mut u64, pair_items: *mut u64) -> c_int;
+    fn capy_plan_tiers2(items_longer_than: *const u32, n_bins: u32, n: u64, max_blocks: u32, total_blocks: u64,
+        sm_count: c_int, warp_items: *mut u64, pair_items: *mut u64, warp_cosched: *mut u32) -> c_int;
+    fn capy_sha3_batch(ctx: *mut CapyCtx, d_bits: c_int, data: *const u8, off: *const u64, n: u64, digests: *mut u8,
+        flags: u32) -> c_int;
+    fn capy_sha3_batch_fixed(ctx: *mut CapyCtx, d_bits: c_int, data: *const u8, msg_len: u64, stride: u64, n: u64,
+        digests: *mut u8, flags: u32) -> c_int;
+    fn capy_sha3_batch_dev(ctx: *mut CapyCtx, dev_index: c_int, stream: *mut c_void, d_bits: c_int,
+        d_data: *const u8, d_off: *const u64, n: u64, d_digests: *mut u8, flags: u32) -> c_int;
+    fn capy_sha3_batch_fixed_dev(ctx: *mut CapyCtx, dev_index: c_int, stream: *mut c_void, d_bits: c_int,
+        d_data: *const u8, msg_len: u64, stride: u64, n: u64, d_digests: *mut u8, flags: u32) -> c_int;
+    fn capy_cshake_batch(ctx: *mut CapyCtx, d_bits: c_int, data: *const u8, off: *const u64, n: u64,
+        fn_name: *const u8, fn_len: u32, custom: *const u8, custom_len: u32, out_bits: u64, out: *mut u8) -> c_int;
+    fn capy_cshake_batch_dev(ctx: *mut CapyCtx, dev_index: c_int, stream: *mut c_void, d_bits: c_int,
+        d_data: *const u8, d_off: *const u64, n: u64, fn_name: *const u8, fn_len: u32, custom: *const u8,
+        custom_len: u32, out_bits: u64, d_out: *mut u8) -> c_int;
+    fn capy_kmac_xof_batch(ctx: *mut CapyCtx, d_bits: c_int, keys: *const u8, key_off: *const u64, data: *const u8,
+        off: *const u64, n: u64, custom: *const u8, custom_len: u32, out_bits: u64, out_off: *const u64,
+        out: *mut u8) -> c_int;
+    fn capy_kmac_xof_batch_dev(ctx: *mut CapyCtx, dev_index: c_int, stream: *mut c_void, d_bits: c_int,
+        d_keys: *const u8, d_key_off: *const u64, d_data: *const u8, d_off: *const u64, n: u64, custom: *const u8,
+        custom_len: u32, out_bits: u64, d_out_off: *const u64, d_out: *mut u8) -> c_int;
+    fn capy_kmac_xof_batch_fixed_dev(ctx: *mut CapyCtx, dev_index: c_int, stream: *mut c_void, d_bits: c_int,
+        d_keys: *const u8, key_len: u64, key_stride: u64, d_data: *const u8, msg_len: u64, msg_stride: u64, n: u64,
+        custom: *const u8, custom_len: u32, out_bits: u64, d_out: *mut u8) -> c_int;
+    fn capy_fips_shake_batch_dev(ctx: *mut CapyCtx, dev_index: c_int, stream: *mut c_void, shake_bits: c_int,
+        d_data: *const u8, d_off: *const u64, n: u64, out_bytes: u64, d_out: *mut u8) -> c_int;
+    fn capy_ed448_fixed_base_batch(ctx: *mut CapyCtx, scalars_be56: *const u8, n: u64, out_xy112: *mut u8) -> c_int;
+    fn capy_ed448_fixed_base_batch_dev(ctx: *mut CapyCtx, dev_index: c_int, stream: *mut c_void,
+        d_scalars_be56: *const u8, n: u64, d_out_xy112: *mut u8) -> c_int;
+    fn capy_ed448_var_base_batch(ctx: *mut CapyCtx, scalars_be56: *const u8, points_xy112: *const u8, n: u64,
+        out_xy112: *mut u8) -> c_int;
+    fn capy_ed448_var_base_batch_dev(ctx: *mut CapyCtx, dev_index: c_int, stream: *mut c_void,
+        d_scalars_be56: *const u8, d_points_xy112: *const u8, n: u64, d_out_xy112: *mut u8,
+        d_bad_flag: *mut c_int) -> c_int;
     fn capy_ed448_keygen_batch(ctx: *mut CapyCtx, d_bits: c_int, pws: *const u8, pw_off: *const u64, n: u64,
-                               out_xy112: *mut u8) -> c_int;
-    fn capy_ed448_sign_batch(ctx: *mut CapyCtx, d_bits: c_int, pws: *const u8, pw_off: *const u64,
-                             msgs: *const u8, msg_off: *const u64, n: u64, h56: *mut u8, z_be56: *mut u8) -> c_int;
+        out_xy112: *mut u8) -> c_int;
+    fn capy_ed448_keygen_batch_dev(ctx: *mut CapyCtx, dev_index: c_int, stream: *mut c_void, d_bits: c_int,
+        d_pws: *const u8, d_pw_off: *const u64, n: u64, d_out_xy112: *mut u8) -> c_int;
+    fn capy_ed448_sign_batch(ctx: *mut CapyCtx, d_bits: c_int, pws: *const u8, pw_off: *const u64, msgs: *const u8,
+        msg_off: *const u64, n: u64, h56: *mut u8, z_be56: *mut u8) -> c_int;
+    fn capy_ed448_sign_batch_dev(ctx: *mut CapyCtx, dev_index: c_int, stream: *mut c_void, d_bits: c_int,
+        d_pws: *const u8, d_pw_off: *const u64, d_msgs: *const u8, d_msg_off: *const u64, n: u64, d_h56: *mut u8,
+        d_z_be56: *mut u8) -> c_int;
     fn capy_ed448_verify_batch(ctx: *mut CapyCtx, d_bits: c_int, pub_xy112: *const u8, msgs: *const u8,
-                               msg_off: *const u64, h56: *const u8, z_be56: *const u8, n: u64, ok: *mut u8) -> c_int;
-    fn capy_sponge_encrypt_batch(ctx: *mut CapyCtx, d_bits: c_int, variant: c_int, pws: *const u8, pw_off: *const u64,
-                                 nonces: *const u8, nonce_len: u64, msgs: *const u8, msg_off: *const u64, n: u64,
-                                 ct: *mut u8, tag64: *mut u8) -> c_int;
-    fn capy_sponge_decrypt_batch(ctx: *mut CapyCtx, d_bits: c_int, variant: c_int, pws: *const u8, pw_off: *const u64,
-                                 nonces: *const u8, nonce_len: u64, ct: *const u8, ct_off: *const u64,
-                                 tag64: *const u8, n: u64, out: *mut u8, ok: *mut u8) -> c_int;
+        msg_off: *const u64, h56: *const u8, z_be56: *const u8, n: u64, ok: *mut u8) -> c_int;
+    fn capy_ed448_verify_batch_dev(ctx: *mut CapyCtx, dev_index: c_int, stream: *mut c_void, d_bits: c_int,
+        d_pub_xy112: *const u8, d_msgs: *const u8, d_msg_off: *const u64, d_h56: *const u8, d_z_be56: *const u8,
+        n: u64, d_ok: *mut u8, d_bad_flag: *mut c_int) -> c_int;
+    fn capy_ed448_ecdh_batch(ctx: *mut CapyCtx, k_rand56: *const u8, pub_xy112: *const u8, n: u64, wx56: *mut u8,
+        z_xy112: *mut u8) -> c_int;
+    fn capy_sponge_encrypt_batch(ctx: *mut CapyCtx, d_bits: c_int, variant: c_int, pws: *const u8,
+        pw_off: *const u64, nonces: *const u8, nonce_len: u64, msgs: *const u8, msg_off: *const u64, n: u64,
+        ct: *mut u8, tag64: *mut u8) -> c_int;
+    fn capy_sponge_decrypt_batch(ctx: *mut CapyCtx, d_bits: c_int, variant: c_int, pws: *const u8,
+        pw_off: *const u64, nonces: *const u8, nonce_len: u64, ct: *const u8, ct_off: *const u64, tag64: *const u8,
+        n: u64, out: *mut u8, ok: *mut u8) -> c_int;
+    fn capy_sponge_encrypt_batch_dev(ctx: *mut CapyCtx, dev_index: c_int, stream: *mut c_void, d_bits: c_int,
+        variant: c_int, d_pws: *const u8, d_pw_off: *const u64, pw_bytes: u64, d_nonces: *const u8, nonce_len: u64,
+        d_msgs: *const u8, d_msg_off: *const u64, n: u64, d_ct: *mut u8, d_tag64: *mut u8) -> c_int;
+    fn capy_sponge_decrypt_batch_dev(ctx: *mut CapyCtx, dev_index: c_int, stream: *mut c_void, d_bits: c_int,
+        variant: c_int, d_pws: *const u8, d_pw_off: *const u64, pw_bytes: u64, d_nonces: *const u8, nonce_len: u64,
+        d_ct: *const u8, d_ct_off: *const u64, d_tag64: *const u8, n: u64, d_out: *mut u8, d_ok: *mut u8) -> c_int;
     fn capy_ed448_key_encrypt_batch(ctx: *mut CapyCtx, d_bits: c_int, pub_xy112: *const u8, k_rand56: *const u8,
-                                    msgs: *const u8, msg_off: *const u64, n: u64, ct: *mut u8, tag56: *mut u8,
-                                    z_xy112: *mut u8) -> c_int;
+        msgs: *const u8, msg_off: *const u64, n: u64, ct: *mut u8, tag56: *mut u8, z_xy112: *mut u8) -> c_int;
     fn capy_ed448_key_decrypt_batch(ctx: *mut CapyCtx, d_bits: c_int, pws: *const u8, pw_off: *const u64,
-                                    z_xy112: *const u8, ct: *const u8, ct_off: *const u64, tag56: *const u8, n: u64,
-                                    out: *mut u8, ok: *mut u8) -> c_int;
+        z_xy112: *const u8, ct: *const u8, ct_off: *const u64, tag56: *const u8, n: u64, out: *mut u8,
+        ok: *mut u8) -> c_int;
+    fn capy_ed448_key_encrypt_batch_dev(ctx: *mut CapyCtx, dev_index: c_int, stream: *mut c_void, d_bits: c_int,
+        d_pub_xy112: *const u8, d_k_rand56: *const u8, d_msgs: *const u8, d_msg_off: *const u64, n: u64,
+        d_ct: *mut u8, d_tag56: *mut u8, d_z_xy112: *mut u8, d_bad_flag: *mut c_int) -> c_int;
+    fn capy_ed448_key_decrypt_batch_dev(ctx: *mut CapyCtx, dev_index: c_int, stream: *mut c_void, d_bits: c_int,
+        d_pws: *const u8, d_pw_off: *const u64, d_z_xy112: *const u8, d_ct: *const u8, d_ct_off: *const u64,
+        d_tag56: *const u8, n: u64, d_out: *mut u8, d_ok: *mut u8, d_bad_flag: *mut c_int) -> c_int;
 }
 
 const CAPY_AE_SHA3: c_int = 0;
@@ -178,14 +243,27 @@ impl Gpu {
             if idx.is_empty() {
                 continue;
             }
-            let (md, mo) = pack(idx.iter().map(|&i| msgs[i].msg.as_slice()));
             let (mut pk, mut h, mut z) = (Vec::new(), Vec::new(), Vec::new());
+            // a signature whose h is not 56 bytes fails on its own and stays out of the fixed-stride batch (one short
+            // field would shift every later item and make the C side read past the Vec)
+            idx.retain(|&i| {
+                let good = msgs[i].sig.as_ref().unwrap().h.len() == 56;
+                if !good {
+                    res[i] = Err(OperationError::SignatureVerificationFailure);
+                }
+                good
+            });
+            if idx.is_empty() {
+                continue;
+            }
             for &i in &idx {
                 let sig = msgs[i].sig.as_ref().unwrap();
                 pk.extend_from_slice(&point_to_xy(&pub_keys[i]));
                 h.extend_from_slice(&sig.h);
                 z.extend_from_slice(&sig.z.val.to_be_bytes());
             }
+            debug_assert!(pk.len() == 112 * idx.len() && h.len() == 56 * idx.len() && z.len() == 56 * idx.len());
+            let (md, mo) = pack(idx.iter().map(|&i| msgs[i].msg.as_slice()));
             let mut ok = vec![0u8; idx.len()];
             let rc = unsafe {
                 capy_ed448_verify_batch(self.ctx, d as c_int, pk.as_ptr(), md.as_ptr(), mo.as_ptr(), h.as_ptr(), z.as_ptr(),
@@ -226,23 +304,24 @@ impl Gpu {
     /// Batched `SpongeEncryptable::sha3_decrypt` (:58-83): on `SHA3DecryptionFailure` the message keeps its ciphertext.
     pub fn sha3_decrypt(&self, msgs: &mut [Message], pws: &[&[u8]]) -> Vec<Result<(), OperationError>> {
         let mut res: Vec<Result<(), OperationError>> = msgs.iter().map(|_| Ok(())).collect();
-        for d in [SecParam::D224, SecParam::D256, SecParam::D384, SecParam::D512] {
-            let mut idx = Vec::new();
-            for (i, m) in msgs.iter().enumerate() {
-                if m.d.is_none() {
-                    res[i] = Err(OperationError::SecurityParameterNotSet);
-                } else if m.sym_nonce.is_none() {
-                    res[i] = Err(OperationError::SymNonceNotSet);
-                } else if m.d == Some(d) {
-                    idx.push(i);
-                }
+        // one C call per (d, nonce length): the C side reads n * nonce_len bytes, so every nonce of a call must have
+        // exactly that length (a deserialized Message may carry any length; the reference would simply derive other keys)
+        let mut groups: std::collections::BTreeMap<(usize, usize), Vec<usize>> = std::collections::BTreeMap::new();
+        for (i, m) in msgs.iter().enumerate() {
+            if m.d.is_none() {
+                res[i] = Err(OperationError::SecurityParameterNotSet);
+            } else if m.sym_nonce.is_none() {
+                res[i] = Err(OperationError::SymNonceNotSet);
+            } else {
+                groups.entry((m.d.unwrap() as usize, m.sym_nonce.as_ref().unwrap().len())).or_default().push(i);
             }
-            if idx.is_empty() {
-                continue;
-            }
+        }
+        for ((d_bits, nonce_len), idx) in groups {
+            let d = SecParam::try_from(d_bits).unwrap();
             let (pd, po) = pack(idx.iter().map(|&i| pws[i]));
             let (cd, co) = pack(idx.iter().map(|&i| msgs[i].msg.as_slice()));
             let z: Vec<u8> = idx.iter().flat_map(|&i| msgs[i].sym_nonce.as_ref().unwrap().iter().copied()).collect();
+            debug_assert!(z.len() == nonce_len * idx.len());
             let mut tags = vec![0u8; idx.len() * 64];
             for (k, &i) in idx.iter().enumerate() {
                 let t = &msgs[i].digest;
@@ -250,7 +329,7 @@ impl Gpu {
             }
             let (mut out, mut ok) = (vec![0u8; cd.len()], vec![0u8; idx.len()]);
             let rc = unsafe {
-                capy_sponge_decrypt_batch(self.ctx, d as c_int, CAPY_AE_SHA3, pd.as_ptr(), po.as_ptr(), z.as_ptr(), 512,
+                capy_sponge_decrypt_batch(self.ctx, d as c_int, CAPY_AE_SHA3, pd.as_ptr(), po.as_ptr(), z.as_ptr(), nonce_len as u64,
                                           cd.as_ptr(), co.as_ptr(), tags.as_ptr(), idx.len() as u64, out.as_mut_ptr(),
                                           ok.as_mut_ptr())
             };
