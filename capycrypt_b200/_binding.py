@@ -42,7 +42,7 @@ SIGNATURES = {
     "capy_launch_count": (u64, [vp]),
     "capy_copy_probe": (i32, [vp, i32, vp, C.c_size_t, vp, C.c_size_t, i32, C.POINTER(C.c_double)]),
     "capy_plan_tiers": (i32, [vp, u32, u64, u32, u64, i32, vp, vp]),
-    "capy_plan_tiers2": (i32, [vp, u32, u64, u32, u64, i32, vp, vp, vp]),
+    "capy_plan_tiers3": (i32, [vp, u32, u64, u32, u64, i32, vp, vp]),
     "capy_gpu_set_plan_cache": (i32, [vp, i32]),
     "capy_sha3_batch": (i32, [vp, i32, u8p, u64p, u64, u8p, u32]),
     "capy_sha3_batch_fixed": (i32, [vp, i32, u8p, u64, u64, u64, u8p, u32]),

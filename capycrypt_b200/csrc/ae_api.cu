@@ -249,7 +249,7 @@ static int dev_key_encrypt(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t st, int d,
   CAPY_SCRATCH(wx, uint8_t, SA_WX, n * 56);
   CAPY_SCRATCH(kw, uint32_t, SA_KW, n * 56);
   // k = 4 * BE(rand) mod r ; W = [k]V (:36-37)
-  int rc = launch_var_base(ctx, st, k_rand, 1, pub, nullptr, proj, bad, n, true);
+  int rc = launch_var_base(ctx, dc, st, k_rand, 1, pub, nullptr, proj, bad, n, true);
   if (rc) return rc;
   rc = launch_to_affine(ctx, st, proj, n, 1, bad, wx);
   if (rc) return rc;
@@ -298,7 +298,7 @@ static int dev_key_decrypt(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t st, int d,
   int rc = launch_kmac_xof(ctx, dc, st, a);
   if (rc) return rc;
   // W = [s]Z (:76)
-  rc = launch_var_base(ctx, st, sk, 1, z_xy, nullptr, proj, bad, n, true);
+  rc = launch_var_base(ctx, dc, st, sk, 1, z_xy, nullptr, proj, bad, n, true);
   if (rc) return rc;
   rc = launch_to_affine(ctx, st, proj, n, 1, bad, wx);
   if (rc) return rc;

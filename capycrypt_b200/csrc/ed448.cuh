@@ -271,8 +271,8 @@ CAPY_HD void pt_fixed_base_mul(PtExt& r, const Sc& k, const uint32_t* __restrict
 // 448-bit value and packed into 14 words: 56 words = 14 uint4 chunks; chunk c of entry e sits at
 // col[(e * 14 + c) * STRIDE], where col already points at this item's column.
 //
-// The whole computation is ONE loop whose body holds one copy of the doubling (4 S + 4 M) and one copy of the
-// addition (9 M), all multiplications inlined: table construction (2P = dbl, jP = (j-1)P + P), the 113 windows
+// The whole computation is ONE loop whose body holds one copy of the doubling (4 S + 3 M, + 1 M for T in the last of a
+// window) and one copy of the addition (8 M, + 1 M for T where an addition follows), all multiplications inlined: table construction (2P = dbl, jP = (j-1)P + P), the 113 windows
 // (4 doublings + 1 addition of a looked-up entry) and the optional addend of verify (U = [z]G + [h]V,
 // ecc/signable.rs:77) are iterations of that loop with different operands, so the accumulator never leaves the
 // registers and no multiplication goes through an out-of-line call.
@@ -434,9 +434,10 @@ CAPY_HD void vb_double(PtExt& r, bool want_t) {
   if (want_t) fe_mul_inl(r.T, E, H);
 }
 
-// r = r + q (add-2008-hwcd, a = 1, q cached with alpha(q.X), alpha(q.Td) <= 2): 9 M.  Ordered so that few field
-// elements are live at a time (the operands of r and q die early): the inlined body fits the registers.
-CAPY_HD void vb_add(PtExt& r, const PtCached& q) {
+// r = r + q (add-2008-hwcd, a = 1, q cached with alpha(q.X), alpha(q.Td) <= 2): 8 M (+ 1 M for T).  Ordered so that few
+// field elements are live at a time (the operands of r and q die early): the inlined body fits the registers.  The
+// additions of the window loop are followed by doublings, which do not read T: they skip that product.
+CAPY_HD void vb_add(PtExt& r, const PtCached& q, bool want_t) {
   Fe A, B, E, H, s1, s2;
   fe_add(s1, r.X, r.Y);       // alpha 2
   fe_add(s2, q.X, q.Y);       // alpha 3
@@ -455,7 +456,7 @@ CAPY_HD void vb_add(PtExt& r, const PtCached& q) {
   fe_mul_inl(r.X, E, F);
   fe_mul_inl(r.Y, G, H);
   fe_mul_inl(r.Z, F, G);
-  fe_mul_inl(r.T, E, H);
+  if (want_t) fe_mul_inl(r.T, E, H);
 }
 
 // r = [k]P (+ addend).  On entry r = P (extended, tight); `load_addend(PtExt&)` is only called when has_addend.
@@ -508,7 +509,8 @@ CAPY_HD void pt_var_base_mul(PtExt& r, const Sc& k, uint4* col, bool CONSTANT_TI
       PtCached e;
       vb_lookup<STRIDE>(e, col, dgt, ct);
       CAPY_BLOCK_SYNC();
-      vb_add(r, e);
+      // T is read by the next addition only: while the table is built, and by the addend after the last window
+      vb_add(r, e, it < 7 || (it == 119 && has_addend));
     }
     if (store_idx >= 0) vb_store_entry<STRIDE>(col, store_idx, r);
   }

@@ -182,7 +182,7 @@ static int dev_var_base(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t st, const uin
   if (n == 0) return CAPY_OK;
   CAPY_SCRATCH(proj, uint32_t, SL_PROJ, n * 256);
   CAPY_SCRATCH(bad, uint8_t, SL_BAD, n);
-  int rc = launch_var_base(ctx, st, d_scalars, 0, d_points, nullptr, proj, bad, n, true);
+  int rc = launch_var_base(ctx, dc, st, d_scalars, 0, d_points, nullptr, proj, bad, n, true);
   if (rc) return rc;
   rc = launch_to_affine(ctx, st, proj, n, 0, bad, d_out_xy);
   if (rc) return rc;
@@ -285,7 +285,7 @@ static int dev_verify(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t st, int d, cons
   if (rc) return rc;
   rc = launch_fixed_base(ctx, dc, st, kw, projA, n, false);
   if (rc) return rc;
-  rc = launch_var_base(ctx, st, d_h, 0, d_pub, projA, projB, bad, n, false);
+  rc = launch_var_base(ctx, dc, st, d_h, 0, d_pub, projA, projB, bad, n, false);
   if (rc) return rc;
   rc = launch_to_affine(ctx, st, projB, n, 1, nullptr, ux);
   if (rc) return rc;
@@ -522,7 +522,7 @@ int capy_ed448_ecdh_batch(capy_ctx* ctx, const uint8_t* k_rand56, const uint8_t*
     if (!d_wx || !proj || !bad || !d_flag) return CAPY_ERR_OOM;
     CAPY_CUDA(ctx, cudaMemsetAsync(d_flag, 0, sizeof(int), st));
     // W = [k]V with k = 4 * BE(rand) mod r (ecc/encryptable.rs:36-37); W.x
-    rc = launch_var_base(ctx, st, d_k, 1, d_pub, nullptr, proj, bad, cnt, true);
+    rc = launch_var_base(ctx, dc, st, d_k, 1, d_pub, nullptr, proj, bad, cnt, true);
     if (rc) return rc;
     rc = launch_to_affine(ctx, st, proj, cnt, 1, bad, d_wx);
     if (rc) return rc;

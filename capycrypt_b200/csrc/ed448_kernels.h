@@ -22,7 +22,8 @@ __device__ __forceinline__ void store_ext(uint32_t* __restrict__ proj, uint64_t 
 int launch_fixed_base(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t st, const uint32_t* k_words, uint32_t* proj, uint64_t n,
                       bool constant_time);
 // ed448_var.cu
-int launch_var_base(capy_ctx* ctx, cudaStream_t st, const uint8_t* scalars, int mode4, const uint8_t* points,
+constexpr int SL_VB_SLABS = 55;  // scratch slot of the per-SM table slabs (24..41 are the pipelines of ed448_api.cu, 56.. the AE ones)
+int launch_var_base(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t st, const uint8_t* scalars, int mode4, const uint8_t* points,
                     const uint32_t* addend, uint32_t* proj, uint8_t* bad, uint64_t n, bool constant_time);
 
 // ed448_api.cu

@@ -40,9 +40,8 @@ constexpr size_t kMaxPrefixEntries = 64;
 struct LaunchPlan {
   const uint32_t* order = nullptr;
   int warps_per_smsp = 0;   // 0 = unthrottled
-  uint64_t warp_items = 0;  // ranks [0, warp_items): one warp per item
-  uint64_t pair_items = 0;  // ranks [warp_items, warp_items + pair_items): two threads per item
-  uint32_t warp_cosched = 1;  // warp-tier chains per scheduler (1..4)
+  uint64_t warp_items[3] = {0, 0, 0};  // one warp per item: [c - 1] of them run c chains per scheduler (ranks in this order)
+  uint64_t pair_items = 0;             // the next ranks: two threads per item
 };
 
 // Cached plan of a ragged batch, keyed by the caller's offsets array (capy_gpu_set_plan_cache): a repeated call with the

@@ -247,30 +247,26 @@ __global__ void len_scatter_kernel(const uint64_t* __restrict__ off, uint64_t n,
   if (i < n) order[atomicAdd(&cursor[len_bin(off, i, stride_bytes)], 1u)] = (uint32_t)i;
 }
 
-// Measured on B200 at one warp per scheduler, per permutation of ONE chain (csrc/keccak_pair_probe.cu in isolation,
-// tools/bench_tier_probe.py inside the sponge on 1 MiB SHA3-512 messages): one thread per state 4.55 / 4.6 us; a thread
-// pair 2.93 / 3.55 us; a whole warp per state 2.18 / 2.19 us.  A warp-tier chain issues only ~32 instructions per
-// ~180-clock round, so several of them can share a scheduler: with c chains per scheduler the 18 shuffles of a round
-// (one warp-wide shuffle per clock per SM) bound the round at 72 c clocks (tools/bench_tier_probe.py, CAPY_WARP_COSCHED).
+// Measured on B200, per permutation of ONE chain inside the sponge (tools/bench_tier_probe.py, 1 MiB SHA3-512 messages,
+// profiles/README.md): one thread per state 4.6 us; a thread pair 3.55 us; a whole warp per state 2.19 us on an otherwise
+// idle GPU and 2.34 us with every SM busy.  A warp-tier chain issues only ~32 instructions per ~180-clock round, so several
+// can share a scheduler -- but the 18 shuffles of its round go through one shuffle unit per SM (one warp-wide shuffle per
+// clock): with c chains per scheduler a round cannot be shorter than 72 c clocks.  Measured: 2.34 / 2.60 / 3.14 us per
+// permutation at c = 1 / 2 / 3.
 constexpr double kPairChainRatio = 3.55 / 4.6;
 constexpr int kMaxWarpCosched = 3;
-#ifndef CAPY_WARP_RATIO_2
-#define CAPY_WARP_RATIO_2 (2.35 / 4.6)
-#endif
-#ifndef CAPY_WARP_RATIO_3
-#define CAPY_WARP_RATIO_3 (2.9 / 4.6)
-#endif
-constexpr double kWarpChainRatio[kMaxWarpCosched + 1] = {0.0, 2.2 / 4.6, CAPY_WARP_RATIO_2, CAPY_WARP_RATIO_3};
+constexpr double kWarpChainRatio[kMaxWarpCosched + 1] = {0.0, 2.34 / 4.6, 2.60 / 4.6, 3.14 / 4.6};
 
 // Tiers of a chain-bound batch.  cum[k] = number of items in length bins > k (bin = whole blocks of the message).
-// Times are in units of one thread-per-state permutation; an SM hosts ONE block: 4 c warp-tier (c chains per
-// scheduler), 64 pair-tier or 128 thread-tier items.  The smallest step time T is searched for which (a) every chain
-// fits its tier, (b) the blocks of the two fast tiers are all resident from the start and (c) the thread tier fits on
-// the SMs that are left; among the co-scheduling factors that reach it the smallest is taken.
+// Times are in units of one thread-per-state permutation; an SM hosts ONE block: 4 c warp-tier items (c = 1, 2 or 3
+// chains per scheduler), 64 pair-tier or 128 thread-tier items.  For a step time T every item takes the cheapest
+// class its chain still fits: warp tier with a scheduler to itself for the longest, then two and three chains per
+// scheduler, then the pair tier, the rest one thread per item.  The smallest T is taken for which (a) the blocks of the
+// fast tiers are all resident from the start and (b) the SM time of all tiers fits 148 T.
 static void plan_tiers(const std::vector<uint32_t>& cum, uint64_t n, uint32_t max_blocks, double total_blocks, int sm_count,
-                       uint64_t* warp_items, uint64_t* pair_items, uint32_t* warp_cosched, int force_c = 0) {
-  *warp_items = *pair_items = 0;
-  *warp_cosched = 1;
+                       uint64_t warp_items[kMaxWarpCosched], uint64_t* pair_items, int force_c = 0) {
+  for (int c = 0; c < kMaxWarpCosched; c++) warp_items[c] = 0;
+  *pair_items = 0;
   const size_t nb = cum.size();
   std::vector<double> work_above(nb);  // blocks in bins > k
   double acc = 0;
@@ -290,27 +286,45 @@ static void plan_tiers(const std::vector<uint32_t>& cum, uint64_t n, uint32_t ma
     *work = work_above[k];
   };
   const double l1 = (double)max_blocks;
-  for (double T = l1 * kWarpChainRatio[1]; T < l1; T *= 1.02) {
-    uint64_t k_fast, k_w;
-    double w_fast, w_w;
-    longer_than(T, &k_fast, &w_fast);                 // must not run one thread per item
-    longer_than(T / kPairChainRatio, &k_w, &w_w);     // must not even run as a pair
-    if (k_w == 0 && T < l1 * kPairChainRatio) continue;  // (the pair tier alone cannot finish the longest item in T)
-    const uint64_t k_p = k_fast - k_w;
-    const int c_lo = force_c >= 1 && force_c <= kMaxWarpCosched ? force_c : 1;
-    const int c_hi = force_c >= 1 && force_c <= kMaxWarpCosched ? force_c : kMaxWarpCosched;
-    for (int c = c_lo; c <= c_hi; c++) {
-      if (k_w && l1 * kWarpChainRatio[c] > T) break;  // the longest chain no longer fits at this sharing factor
-      const uint64_t blocks = (k_w + 4 * c - 1) / (4 * c) + (k_p + 63) / 64;
-      if (blocks + 1 > (uint64_t)sm_count) continue;
-      // the thread-per-item tier gets the SMs the fast tiers leave (those stay busy for about T: their items are the
-      // longest); its items are dispatched longest first, so it needs its share of SMs from the start
-      if ((total_blocks - w_fast) / 128.0 > T * (double)((uint64_t)sm_count - blocks)) continue;
-      *warp_items = k_w;
-      *pair_items = k_p;
-      *warp_cosched = (uint32_t)c;
-      return;
+  const int c_first = force_c >= 1 && force_c <= kMaxWarpCosched ? force_c : 1;
+  for (double T = l1 * kWarpChainRatio[c_first]; T < l1; T *= 1.01) {
+    // class boundaries: an item with chain L runs c chains per scheduler iff L * ratio[c] <= T < L * ratio[c + 1]
+    uint64_t k_above[kMaxWarpCosched + 2];  // [c] = items too long for warp class c + 1 (and every cheaper class)
+    double w_above[kMaxWarpCosched + 2];
+    k_above[0] = 0;
+    w_above[0] = 0;
+    for (int c = 1; c <= kMaxWarpCosched; c++) {
+      const int next = c + 1;
+      const double ratio = next <= kMaxWarpCosched ? kWarpChainRatio[next] : kPairChainRatio;
+      longer_than(T / ratio, &k_above[c], &w_above[c]);
+      if (force_c && c != force_c) {  // diagnostics: one warp class only
+        k_above[c] = c < force_c ? 0 : k_above[force_c];
+        w_above[c] = c < force_c ? 0 : w_above[force_c];
+      }
     }
+    uint64_t k_fast;
+    double w_fast;
+    longer_than(T, &k_fast, &w_fast);  // must not run one thread per item
+    if (k_above[kMaxWarpCosched] == 0 && T < l1 * kPairChainRatio) continue;  // the pair tier alone cannot finish the longest in T
+    uint64_t blocks = 0;
+    double sm_time = 0;  // in units of (thread-tier permutation x SM)
+    uint64_t cnt[kMaxWarpCosched];
+    for (int c = 1; c <= kMaxWarpCosched; c++) {
+      cnt[c - 1] = k_above[c] - k_above[c - 1];
+      blocks += (cnt[c - 1] + 4 * c - 1) / (4 * c);
+      sm_time += (w_above[c] - w_above[c - 1]) * kWarpChainRatio[c] / (4.0 * c);
+    }
+    const uint64_t k_p = k_fast - k_above[kMaxWarpCosched];
+    blocks += (k_p + 63) / 64;
+    sm_time += (w_fast - w_above[kMaxWarpCosched]) * kPairChainRatio / 64.0 + (total_blocks - w_fast) / 128.0;
+    if (blocks + 1 > (uint64_t)sm_count) continue;
+    if (sm_time > 0.95 * T * (double)sm_count) continue;
+    // the thread-per-item tier gets the SMs the fast tiers leave (those stay busy for about T: their items are the
+    // longest); its items are dispatched longest first, so it needs its share of SMs from the start
+    if ((total_blocks - w_fast) / 128.0 > T * (double)((uint64_t)sm_count - blocks)) continue;
+    for (int c = 0; c < kMaxWarpCosched; c++) warp_items[c] = cnt[c];
+    *pair_items = k_p;
+    return;
   }
 }
 
@@ -381,8 +395,7 @@ static int plan_ragged(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t st, const uint
     std::vector<uint32_t> cum(kLenBins);  // after the scan hist[k] = number of items in bins > k
     PLAN_CUDA(cudaMemcpyAsync(cum.data(), hist, (size_t)kLenBins * 4, cudaMemcpyDeviceToHost, st));
     PLAN_CUDA(cudaStreamSynchronize(st));
-    plan_tiers(cum, n, max_blocks, (double)total_blocks, dc.sm_count, &plan->warp_items, &plan->pair_items,
-               &plan->warp_cosched, force_c);
+    plan_tiers(cum, n, max_blocks, (double)total_blocks, dc.sm_count, plan->warp_items, &plan->pair_items, force_c);
   }
   if (bins > 1) {  // (uniform lengths: nothing to order)
     len_scatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_off, n, stride_bytes, hist, order);
@@ -424,18 +437,27 @@ static int plan_ragged(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t st, const uint
 
 template <int LANES>
 static int launch_sponge_t(capy_ctx* ctx, cudaStream_t stream, SpongeJob J, unsigned block, const LaunchPlan& plan) {
-  const uint64_t warp_items = plan.warp_items, pair_items = plan.pair_items;
+  const uint64_t warp_items = plan.warp_items[0] + plan.warp_items[1] + plan.warp_items[2], pair_items = plan.pair_items;
   if (pair_items || warp_items) {
-    // chain-bound batch: warp blocks, then pair blocks, then thread-per-item blocks, one block per SM.  A block has
-    // 128 c threads: the warp tier runs c chains per scheduler, the other tiers use the first four warps only.
-    const unsigned c = std::max(1u, std::min<unsigned>(plan.warp_cosched, kMaxWarpCosched));
-    const unsigned warp_blocks = grid_for(warp_items, 4 * c);
-    const unsigned pair_blocks = grid_for(2 * pair_items, 128);
+    // chain-bound batch: warp blocks (one, two, three chains per scheduler), then pair blocks, then thread-per-item
+    // blocks, one block per SM.  A block has 384 threads: a warp-tier block of class c uses 4 c warps, the other tiers
+    // the first four; the rest exit at once.
+    SpongeTiers tiers;
+    uint32_t warp_blocks = 0;
+    uint64_t rank = 0;
+    for (int c = 0; c < 3; c++) {
+      tiers.first_block[c] = warp_blocks;
+      tiers.first_rank[c] = rank;
+      warp_blocks += grid_for(plan.warp_items[c], 4 * (c + 1));
+      rank += plan.warp_items[c];
+    }
+    tiers.warp_blocks = warp_blocks;
+    tiers.pair_blocks = grid_for(2 * pair_items, 128);
     const unsigned solo_blocks = grid_for(J.n - pair_items - warp_items, 128);
     J.warp_items = warp_items;
     J.first = warp_items + pair_items;
     CAPY_CUDA(ctx, cudaFuncSetAttribute(sponge_tiered_kernel<LANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-    sponge_tiered_kernel<LANES><<<warp_blocks + pair_blocks + solo_blocks, 128 * c, 226 * 1024, stream>>>(J, warp_blocks, pair_blocks);
+    sponge_tiered_kernel<LANES><<<warp_blocks + tiers.pair_blocks + solo_blocks, 384, 226 * 1024, stream>>>(J, tiers);
     ctx->launches++;
     CAPY_CUDA(ctx, cudaGetLastError());
     return CAPY_OK;
@@ -793,7 +815,7 @@ int launch_kmac_xof2(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t stream, const Km
   if (rc) return rc;
   JA.order = JB.order = plan.order;
   const int lanes = (int)(bytepad_value(a.d_bits) * 8 / 64);
-  if (plan.warp_items || plan.pair_items) {
+  if (plan.warp_items[0] || plan.warp_items[1] || plan.warp_items[2] || plan.pair_items) {
     rc = launch_sponge(ctx, dc, stream, lanes, JA, plan);
     if (rc) return rc;
     return launch_sponge(ctx, dc, stream, lanes, JB, plan);
@@ -818,15 +840,17 @@ extern "C" {
 // =================================================================================================
 int capy_plan_tiers(const uint32_t* items_longer_than, uint32_t n_bins, uint64_t n, uint32_t max_blocks, uint64_t total_blocks,
                     int sm_count, uint64_t* warp_items, uint64_t* pair_items) {
-  uint32_t c;
-  return capy_plan_tiers2(items_longer_than, n_bins, n, max_blocks, total_blocks, sm_count, warp_items, pair_items, &c);
+  uint64_t w[3];
+  int rc = capy_plan_tiers3(items_longer_than, n_bins, n, max_blocks, total_blocks, sm_count, w, pair_items);
+  if (rc == CAPY_OK && warp_items) *warp_items = w[0] + w[1] + w[2];
+  return warp_items ? rc : CAPY_ERR_BAD_ARG;
 }
 
-int capy_plan_tiers2(const uint32_t* items_longer_than, uint32_t n_bins, uint64_t n, uint32_t max_blocks, uint64_t total_blocks,
-                     int sm_count, uint64_t* warp_items, uint64_t* pair_items, uint32_t* warp_cosched) {
-  if (!items_longer_than || !n_bins || !warp_items || !pair_items || !warp_cosched || sm_count < 2) return CAPY_ERR_BAD_ARG;
+int capy_plan_tiers3(const uint32_t* items_longer_than, uint32_t n_bins, uint64_t n, uint32_t max_blocks, uint64_t total_blocks,
+                     int sm_count, uint64_t* warp_items_by_sharing, uint64_t* pair_items) {
+  if (!items_longer_than || !n_bins || !warp_items_by_sharing || !pair_items || sm_count < 2) return CAPY_ERR_BAD_ARG;
   std::vector<uint32_t> cum(items_longer_than, items_longer_than + n_bins);
-  plan_tiers(cum, n, max_blocks, (double)total_blocks, sm_count, warp_items, pair_items, warp_cosched);
+  plan_tiers(cum, n, max_blocks, (double)total_blocks, sm_count, warp_items_by_sharing, pair_items);
   return CAPY_OK;
 }
 

@@ -609,13 +609,23 @@ __device__ __noinline__ void sponge_item_pair_ool(const SpongeJob& J, uint64_t i
   sponge_item_pair<LANES>(J, i, valid, half);
 }
 
+// block ranges of the warp tier: class c (c + 1 chains per scheduler) owns blocks [first_block[c], first_block[c + 1])
+// (the last class ends at warp_blocks) and the ranks from first_rank[c], 4 (c + 1) per block
+struct SpongeTiers {
+  uint32_t first_block[3];
+  uint64_t first_rank[3];
+  uint32_t warp_blocks, pair_blocks;
+};
+
 template <int LANES>
-__global__ void __launch_bounds__(384, 1) sponge_tiered_kernel(const SpongeJob J, uint32_t warp_blocks, uint32_t pair_blocks) {
+__global__ void __launch_bounds__(384, 1) sponge_tiered_kernel(const SpongeJob J, const SpongeTiers tiers) {
   // __launch_bounds__(.., 1): with the default bound ptxas held the kernel at 128 registers and, once the unrolled
   // warp-tier permutation was part of it, scheduled the (instruction-for-instruction identical) round loop of the
   // thread tier differently: 5.4 instead of 4.6 us per permutation at one warp per scheduler.
-  // blockDim.x = 128 c: the warp tier runs c chains per scheduler (a warp-tier chain issues ~32 instructions per
-  // ~180-clock round), the pair and thread tiers want a scheduler per warp and use the first four warps only.
+  // blockDim.x = 384: a warp-tier block of class c runs 4 c chains (a warp-tier chain issues ~32 instructions per
+  // ~180-clock round, so up to three share a scheduler), the pair and thread tiers want a scheduler per warp and use the
+  // first four warps only; warps without work exit at once.
+  const uint32_t warp_blocks = tiers.warp_blocks, pair_blocks = tiers.pair_blocks;
   if (blockIdx.x >= warp_blocks) {
     if (threadIdx.x >= 128) return;
     if (blockIdx.x >= warp_blocks + pair_blocks) {
@@ -629,8 +639,12 @@ __global__ void __launch_bounds__(384, 1) sponge_tiered_kernel(const SpongeJob J
       sponge_item_pair_ool<LANES>(J, valid ? sponge_rank_item(J, r) : 0, valid, (uint32_t)(t & 1));
     }
   } else {
-    const uint64_t r = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (r >= J.warp_items) return;  // whole warps leave together
+    const int c = blockIdx.x >= tiers.first_block[2] ? 2 : blockIdx.x >= tiers.first_block[1] ? 1 : 0;
+    const uint32_t per_block = 4u * (c + 1), w = threadIdx.x >> 5;
+    if (w >= per_block) return;
+    const uint64_t r = tiers.first_rank[c] + (uint64_t)(blockIdx.x - tiers.first_block[c]) * per_block + w;
+    const uint64_t end = c < 2 ? tiers.first_rank[c + 1] : J.warp_items;
+    if (r >= end) return;  // whole warps leave together
     sponge_item_warp<LANES>(J, sponge_rank_item(J, r));
   }
 }

@@ -103,11 +103,11 @@ int capy_gpu_set_plan_cache(capy_ctx* ctx, int enable);
  * warp per item and how many of the next with two threads per item (DESIGN.md "chain-bound batches"). */
 int capy_plan_tiers(const uint32_t* items_longer_than, uint32_t n_bins, uint64_t n, uint32_t max_blocks,
                     uint64_t total_blocks, int sm_count, uint64_t* warp_items, uint64_t* pair_items);
-/* same, and how many warp-tier chains share a warp scheduler (1..3): a warp-tier chain uses a fraction of its
- * scheduler's issue slots, so a batch with more long messages than schedulers co-schedules them */
-int capy_plan_tiers2(const uint32_t* items_longer_than, uint32_t n_bins, uint64_t n, uint32_t max_blocks,
-                     uint64_t total_blocks, int sm_count, uint64_t* warp_items, uint64_t* pair_items,
-                     uint32_t* warp_cosched);
+/* same, with the warp-per-item count split by how many such chains share a warp scheduler: warp_items_by_sharing[c - 1]
+ * items run c chains per scheduler, c = 1..3 (a warp-tier chain uses a fraction of its scheduler's issue slots; the
+ * longest chains get a scheduler to themselves, the next ones share) */
+int capy_plan_tiers3(const uint32_t* items_longer_than, uint32_t n_bins, uint64_t n, uint32_t max_blocks,
+                     uint64_t total_blocks, int sm_count, uint64_t* warp_items_by_sharing, uint64_t* pair_items);
 
 /* ---- SHA3-d : SpongeHashable::compute_sha3_hash (sha3/hashable.rs:19-21 -> shake,
  *      sha3/shake_functions.rs:24-32 -> sponge_absorb/squeeze, sha3/sponge.rs:10-34) ------- */
