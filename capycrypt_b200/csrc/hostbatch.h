@@ -48,6 +48,88 @@ inline std::vector<Range> split_items(const uint64_t* off, uint64_t fixed_len, u
   return r;
 }
 
+// ---- ragged sponge batches over several devices: longest-processing-time-first over the chains --------
+// A sponge is sequential per message, so a device cannot finish before its longest message has, and a contiguous split
+// by bytes can hand one device most of the long chains (a batch sorted by length does).  The outliers -- messages that
+// cost at least 8 x the average, at most kLptMaxLong of them -- are dealt out longest first, each to the device with
+// the least work so far (LPT); the remaining messages follow in contiguous index ranges that top every device up to the
+// same load, so the bulk of the batch still moves with one copy per range.  A device's share is a list of runs of
+// consecutive items in increasing index order.
+struct Run {
+  uint64_t i0, i1;
+};
+struct DeviceShare {
+  std::vector<Run> runs;
+  uint64_t items = 0, bytes = 0, cost = 0;
+};
+constexpr size_t kLptMaxLong = 4096;
+
+inline std::vector<DeviceShare> lpt_shares(const uint64_t* off, uint64_t n, size_t parts, uint32_t unit_bytes,
+                                           uint64_t per_item_cost) {
+  parts = std::max<size_t>(1, std::min<uint64_t>(parts, std::max<uint64_t>(n, 1)));
+  std::vector<DeviceShare> sh(parts);
+  if (n == 0) return sh;
+  auto cost_of = [&](uint64_t i) -> uint64_t { return (off[i + 1] - off[i]) / unit_bytes + per_item_cost; };
+  uint64_t total = 0;
+  for (uint64_t i = 0; i < n; i++) total += cost_of(i);
+  // outliers: cost >= 8 x average (only then can a single chain matter for the balance)
+  const uint64_t thr = std::max<uint64_t>(8 * (total / n), per_item_cost + 1);
+  std::vector<std::pair<uint64_t, uint64_t>> longs;  // (cost, index)
+  if (parts > 1)
+    for (uint64_t i = 0; i < n; i++) {
+      const uint64_t c = cost_of(i);
+      if (c >= thr) longs.emplace_back(c, i);
+    }
+  std::sort(longs.begin(), longs.end(), [](const auto& a, const auto& b) { return a.first != b.first ? a.first > b.first : a.second < b.second; });
+  if (longs.size() > kLptMaxLong) longs.resize(kLptMaxLong);
+  std::vector<uint64_t> load(parts, 0);
+  std::vector<std::pair<uint64_t, uint32_t>> owner;  // (index, device) of the dealt-out items, sorted by index below
+  owner.reserve(longs.size());
+  for (const auto& l : longs) {
+    size_t best = 0;
+    for (size_t d = 1; d < parts; d++)
+      if (load[d] < load[best]) best = d;
+    load[best] += l.first;
+    owner.emplace_back(l.second, (uint32_t)best);
+  }
+  std::sort(owner.begin(), owner.end());
+  // everything else: contiguous ranges, every device topped up to total / parts
+  auto push = [&](size_t d, uint64_t i) {
+    DeviceShare& s = sh[d];
+    if (!s.runs.empty() && s.runs.back().i1 == i) s.runs.back().i1 = i + 1;
+    else s.runs.push_back({i, i + 1});
+    s.items++;
+    s.bytes += off[i + 1] - off[i];
+    s.cost += cost_of(i);
+  };
+  // short-item budget of every device: what it lacks to total / parts, rescaled so that the budgets add up to the
+  // cost of the short items; device d takes the short items whose running cost falls into its slice of that sum
+  uint64_t long_total = 0;
+  for (uint64_t l : load) long_total += l;
+  const double rest = (double)(total - long_total), target = (double)total / (double)parts;
+  std::vector<double> bound(parts);
+  double lack = 0;
+  for (size_t d = 0; d < parts; d++) lack += std::max(0.0, target - (double)load[d]);
+  double accb = 0;
+  for (size_t d = 0; d < parts; d++) {
+    accb += lack > 0 ? std::max(0.0, target - (double)load[d]) * rest / lack : rest / (double)parts;
+    bound[d] = accb;
+  }
+  size_t cur = 0, next_long = 0;
+  double acc = 0;
+  for (uint64_t i = 0; i < n; i++) {
+    if (next_long < owner.size() && owner[next_long].first == i) {
+      push(owner[next_long].second, i);
+      next_long++;
+      continue;
+    }
+    while (cur + 1 < parts && acc >= bound[cur]) cur++;
+    push(cur, i);
+    acc += (double)cost_of(i);
+  }
+  return sh;
+}
+
 // Runs fn(device, shard) for every shard: inline on the caller's thread for a single shard, else on the devices'
 // persistent worker threads (DeviceWorker), each holding its device's lock for the duration of its closure.
 template <class F>

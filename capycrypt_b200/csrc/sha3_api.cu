@@ -854,6 +854,16 @@ int capy_plan_tiers3(const uint32_t* items_longer_than, uint32_t n_bins, uint64_
   return CAPY_OK;
 }
 
+int capy_lpt_shares(const uint64_t* off, uint64_t n, uint32_t parts, uint32_t unit_bytes, uint64_t per_item_cost,
+                    uint32_t* owner) {
+  if (!off || !owner || parts == 0 || unit_bytes == 0) return CAPY_ERR_BAD_ARG;
+  auto shares = lpt_shares(off, n, parts, unit_bytes, per_item_cost);
+  for (size_t d = 0; d < shares.size(); d++)
+    for (const Run& r : shares[d].runs)
+      for (uint64_t i = r.i0; i < r.i1; i++) owner[i] = (uint32_t)d;
+  return CAPY_OK;
+}
+
 // =================================================================================================
 // SHA3-d
 // =================================================================================================
@@ -882,6 +892,47 @@ int capy_sha3_batch(capy_ctx* ctx, int d_bits, const uint8_t* data, const uint64
   if (!valid_secparam(d_bits)) return CAPY_ERR_BAD_SECPARAM;
   if (n == 0) return CAPY_OK;
   const size_t ob = (size_t)d_bits / 8;
+  if (ctx->devs.size() > 1) {
+    // several devices: the outliers of the batch (long chains) are dealt out longest first, the rest follows in
+    // contiguous ranges (lpt_shares).  When nothing had to be dealt out every share is one run and the plain path
+    // below does the same thing with pipelined chunks.
+    const uint32_t rate = (1600 - sha3_capacity(d_bits)) / 8;
+    auto shares = lpt_shares(off, n, ctx->devs.size(), rate, 2);
+    bool scattered = false;
+    for (const DeviceShare& s : shares) scattered |= s.runs.size() > 1;
+    if (scattered) {
+      std::vector<Range> slots;
+      for (size_t k = 0; k < shares.size(); k++) slots.push_back({k, k + 1});  // for_each_device: one closure per device
+      return for_each_device(ctx, slots, [&](DeviceCtx& dc, Range slot) -> int {
+        const DeviceShare& sh = shares[slot.i0];
+        if (sh.items == 0) return CAPY_OK;
+        cudaStream_t st = dc.streams[0];
+        uint8_t* d_data = (uint8_t*)scratch_get(dc, 0, (size_t)sh.bytes + 16);
+        uint64_t* d_off = (uint64_t*)scratch_get(dc, 1, (size_t)(sh.items + 1) * 8);
+        uint8_t* d_out = (uint8_t*)scratch_get(dc, 2, (size_t)sh.items * ob);
+        if (!d_data || !d_off || !d_out) return CAPY_ERR_OOM;
+        std::vector<uint64_t> loc(sh.items + 1);  // offsets of this device's items in its own packed buffer
+        uint64_t at = 0, j = 0;
+        for (const Run& r : sh.runs) {  // one copy per run of consecutive messages
+          const uint64_t b0 = off[r.i0], b1 = off[r.i1];
+          if (b1 > b0) CAPY_CUDA(ctx, cudaMemcpyAsync(d_data + at, data + b0, (size_t)(b1 - b0), cudaMemcpyHostToDevice, st));
+          for (uint64_t i = r.i0; i < r.i1; i++) loc[j++] = at + (off[i] - b0);
+          at += b1 - b0;
+        }
+        loc[j] = at;
+        CAPY_CUDA(ctx, cudaMemcpyAsync(d_off, loc.data(), (size_t)(sh.items + 1) * 8, cudaMemcpyHostToDevice, st));
+        int rc = launch_sha3(ctx, dc, st, d_bits, d_data, d_off, 0, 0, sh.items, d_out, flags);
+        if (rc) return rc;
+        j = 0;
+        for (const Run& r : sh.runs) {  // the digests of a run are consecutive on both sides
+          CAPY_CUDA(ctx, cudaMemcpyAsync(digests + r.i0 * ob, d_out + j * ob, (size_t)(r.i1 - r.i0) * ob, cudaMemcpyDeviceToHost, st));
+          j += r.i1 - r.i0;
+        }
+        CAPY_CUDA(ctx, cudaStreamSynchronize(st));  // (`loc` stays alive until here)
+        return CAPY_OK;
+      });
+    }
+  }
   auto shards = split_items(off, 0, 0, n, ctx->devs.size(), 200);
   return for_each_device(ctx, shards, [&](DeviceCtx& dc, Range sh) -> int {
     // long messages: few big chunks, so that the longest-first schedule sees enough work beside them

@@ -109,6 +109,14 @@ int capy_plan_tiers(const uint32_t* items_longer_than, uint32_t n_bins, uint64_t
 int capy_plan_tiers3(const uint32_t* items_longer_than, uint32_t n_bins, uint64_t n, uint32_t max_blocks,
                      uint64_t total_blocks, int sm_count, uint64_t* warp_items_by_sharing, uint64_t* pair_items);
 
+/* ---- diagnostics: how a ragged sponge batch is divided over the devices of a ctx (no GPU needed) ------------------- */
+/* owner[i] = index of the device that hashes item i when capy_sha3_batch runs on a ctx of `parts` devices: the outliers
+ * (messages that cost >= 8 x the average, cost = len / unit_bytes + per_item_cost permutations) are dealt out longest
+ * first to the least loaded device (LPT over the chains), the rest follows in contiguous index ranges that
+ * top every device up to the same load. */
+int capy_lpt_shares(const uint64_t* off, uint64_t n, uint32_t parts, uint32_t unit_bytes, uint64_t per_item_cost,
+                    uint32_t* owner);
+
 /* ---- SHA3-d : SpongeHashable::compute_sha3_hash (sha3/hashable.rs:19-21 -> shake,
  *      sha3/shake_functions.rs:24-32 -> sponge_absorb/squeeze, sha3/sponge.rs:10-34) ------- */
 /* digests: n * (d_bits/8) bytes, item-major.  Hashes the ORIGINAL bytes of every message (the

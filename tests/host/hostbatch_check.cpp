@@ -47,6 +47,43 @@ int main() {
   std::vector<uint64_t> small(1 << 20 | 1, 0);
   for (size_t i = 1; i < small.size(); i++) small[i] = small[i - 1] + 64;  // 2^20 x 64 B
   EXPECT(ragged_chunk_count(small.data(), 0, 1 << 20, 0) == 8);
+  // ---- LPT shares of a ragged batch over several devices ----
+  {
+    // a batch sorted by length, longest first: a contiguous split by bytes gives device 0 all the long chains
+    std::vector<uint64_t> so(1 + 40 + 100000, 0);
+    for (int i = 1; i <= 40; i++) so[i] = so[i - 1] + (1u << 20);
+    for (size_t i = 41; i < so.size(); i++) so[i] = so[i - 1] + 400;
+    const uint64_t n = so.size() - 1;
+    for (size_t parts : {2, 4, 8}) {
+      auto sh = lpt_shares(so.data(), n, parts, 72, 2);
+      EXPECT(sh.size() == parts);
+      std::vector<int> seen(n, 0);
+      uint64_t max_cost = 0, sum_cost = 0, max_long = 0, min_long = ~0ull;
+      for (const DeviceShare& d : sh) {
+        uint64_t prev = 0, longs = 0, items = 0;
+        for (const Run& r : d.runs) {
+          EXPECT(r.i0 < r.i1 && r.i0 >= prev);  // increasing, non-overlapping
+          prev = r.i1;
+          for (uint64_t i = r.i0; i < r.i1; i++) { seen[i]++; items++; if (i < 40) longs++; }
+        }
+        EXPECT(items == d.items);
+        max_cost = std::max(max_cost, d.cost);
+        sum_cost += d.cost;
+        max_long = std::max(max_long, longs);
+        min_long = std::min(min_long, longs);
+        EXPECT(d.runs.size() <= 64);  // a handful of copies per device, not one per message
+      }
+      for (uint64_t i = 0; i < n; i++) EXPECT(seen[i] == 1);  // a partition
+      EXPECT(max_long - min_long <= 1);                        // the long chains are dealt out evenly
+      EXPECT(max_cost * parts <= sum_cost + sum_cost / 20 + parts * 15000);  // and the total work is balanced
+    }
+    // uniform batch: no outliers -> plain contiguous ranges, one run per device
+    auto sh = lpt_shares(small.data(), 1 << 20, 4, 136, 1);
+    for (const DeviceShare& d : sh) EXPECT(d.runs.size() == 1 && d.items == (1u << 18));
+    // fewer items than devices, empty batch
+    EXPECT(lpt_shares(so.data(), 3, 8, 72, 2).size() == 3);
+    EXPECT(lpt_shares(so.data(), 0, 4, 72, 2).size() == 1);
+  }
   printf("hostbatch ok\n");
   return 0;
 }

@@ -57,3 +57,24 @@ def test_multi_device_ctx_matches_single(engine, oracle):
     rc, out, ok = eng2.ed448_key_decrypt(pws, po, z2, c2, mo, t2, 512)
     assert rc == 0 and ok.all() and np.array_equal(out, md)
     eng2.close()
+
+
+@pytest.mark.skipif("_ndev() < 2")
+def test_multi_device_ctx_deals_out_long_messages(engine, oracle):
+    """A ragged batch with outliers, in an order that is unkind to a contiguous split (all long messages first): the
+    multi-device ctx deals the long chains out over its devices (lpt_shares) and still returns the digests in the
+    caller's order, identical to a single-GPU ctx and to the oracle."""
+    eng2 = Engine(devices=list(range(min(_ndev(), 8))))
+    rnd = np.random.default_rng(9)
+    lens = np.concatenate([rnd.integers(200_000, 600_000, size=37), rnd.integers(0, 800, size=30000),
+                           rnd.integers(300_000, 500_000, size=5), [0, 71, 135, 72 * 3000 - 1]])
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    data = rnd.integers(0, 256, size=int(off[-1]), dtype=np.uint8)
+    for d in (256, 512):
+        a = engine.sha3(data, off, d)
+        b = eng2.sha3(data, off, d)
+        assert np.array_equal(a, b), d
+    idx = np.concatenate([np.arange(40), rnd.choice(len(lens), 200, replace=False), np.arange(len(lens) - 9, len(lens))])
+    d2, o2 = pack([data[int(off[i]):int(off[i + 1])].tobytes() for i in idx])
+    assert np.array_equal(b[idx], oracle.sha3_batch(d2, o2, 512, threads=0))
+    eng2.close()
