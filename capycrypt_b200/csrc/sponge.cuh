@@ -322,10 +322,31 @@ __device__ __forceinline__ void sponge_item(const SpongeJob& J, uint64_t i) {
   const uint64_t sq_bytes = 8ull * J.sq_lanes;
   const uint8_t* xi = J.xor_in ? J.xor_in + (o - J.out) : nullptr;
   const bool o_aligned = (reinterpret_cast<uintptr_t>(o) & 7u) == 0 && (!xi || (reinterpret_cast<uintptr_t>(xi) & 7u) == 0);
+  // keystream shape (out = squeeze ^ xor_in, sha3/encryptable.rs:41-42) with whole aligned blocks of LANES lanes: the
+  // words of xor_in for the NEXT block are loaded before the permutation, like the absorb loop does with the message
+  // (the loads of a block used to sit right in front of the XOR that needs them: long_scoreboard 0.52 in the seal).
+  const bool xor_pipelined = xi && o_aligned && (int)J.sq_lanes == LANES;
+  uint2 xm[LANES];
+  if (xor_pipelined && sq_bytes <= out_bytes) {
+#pragma unroll
+    for (int j = 0; j < LANES; j++) xm[j] = reinterpret_cast<const uint2*>(xi)[j];
+  }
   for (uint64_t produced = 0; produced < out_bytes;) {
     if (o_aligned && produced + sq_bytes <= out_bytes) {
       // whole squeeze block, 8-byte aligned: straight stores (the keystream / long-output shape)
       uint2* op = reinterpret_cast<uint2*>(o + produced);
+      if (xor_pipelined) {
+#pragma unroll
+        for (int j = 0; j < LANES; j++) op[j] = make_uint2(a[j].lo ^ xm[j].x, a[j].hi ^ xm[j].y);
+        produced += sq_bytes;
+        if (produced + sq_bytes <= out_bytes) {
+          const uint2* xp = reinterpret_cast<const uint2*>(xi + produced);
+#pragma unroll
+          for (int j = 0; j < LANES; j++) xm[j] = xp[j];
+        }
+        if (produced < out_bytes) keccak_f1600(a);
+        continue;
+      }
       const uint2* xp = reinterpret_cast<const uint2*>(xi ? xi + produced : nullptr);
 #pragma unroll
       for (int j = 0; j < 21; j++) {

@@ -6,14 +6,15 @@ TAG=${1:-rXX}
 O=gpurun_out
 mkdir -p $O
 python bench.py --steps 20 --warmup 3 --no-cpu > $O/bench_${TAG}_plain.json 2> $O/bench_${TAG}_plain.err || exit 1
-ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file $O/${TAG}_bench_launches_ncu.csv \
+ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file $O/${TAG}_bench_launches_ncu.csv \
     python bench.py --steps 20 --warmup 3 --no-cpu > $O/ncu_${TAG}_launches.log 2>&1
 cap() {  # name, kernel regex, skip
   ncu --set full --clock-control none --import-source on -k regex:$2 -s $3 -c 1 -o $O/prof_${TAG}_$1 -f \
       python bench.py --steps 20 --warmup 3 --no-cpu > $O/ncu_${TAG}_$1.log 2>&1
 }
 cap sha3_short sha3_short 5
-cap sponge_kmac 'sponge_kernel' 2
+cap sponge_kmac 'sponge_kernel<' 2
+cap sponge_ae 'sponge_kernel2' 1
 cap sponge_tiered sponge_tiered 0
 cap fixed_base fixed_base_kernel 1
 cap var_base var_base_kernel 1
