@@ -283,7 +283,14 @@ constexpr int VB_ENTRIES = 8;
 constexpr int VB_CHUNKS = 14;  // uint4 chunks per entry: X | Y | Z | d*T, 14 words each
 
 #if defined(__CUDA_ARCH__)
+// With the table in local memory (round 1) a block barrier in front of every doubling / addition paid off: the warps of
+// a block fetched one instruction stream.  Since the table moved to shared memory / the L2 the barrier costs more than
+// the drift (29.5 against 31.2 ms per 2^18 items, profiles/README.md round 2): off unless CAPY_VB_SYNC is defined.
+#if defined(CAPY_VB_SYNC)
 #define CAPY_BLOCK_SYNC() __syncthreads()
+#else
+#define CAPY_BLOCK_SYNC() ((void)0)
+#endif
 CAPY_HD uint32_t capy_fshr(uint32_t lo, uint32_t hi, uint32_t sh) { return __funnelshift_r(lo, hi, sh); }
 CAPY_HD uint32_t capy_fshl(uint32_t lo, uint32_t hi, uint32_t sh) { return __funnelshift_l(lo, hi, sh); }
 #else
@@ -372,17 +379,27 @@ CAPY_HD void vb_lookup(PtCached& e, const uint4* col, int dgt, bool CONSTANT_TIM
   if (CONSTANT_TIME) {
 #pragma unroll
     for (int k = 0; k < 56; k++) w[k] = 0;
-#pragma unroll 1
-    for (uint32_t j = 1; j <= (uint32_t)VB_ENTRIES; j++) {
-      const uint32_t m = (j == mag) ? 0xffffffffu : 0u;
-      const uint4* ent = col + (size_t)(j - 1) * VB_CHUNKS * STRIDE;
+    // software pipeline over half entries (7 chunks): the loads of the next half are in flight while the current one is
+    // masked in -- the second four warps of a block read their table from the L2 (~400 clocks per dependent batch)
+    constexpr int HALF = VB_CHUNKS / 2;
+    uint4 buf[2][HALF];
 #pragma unroll
-      for (int c = 0; c < VB_CHUNKS; c++) {
-        const uint4 v = ent[c * STRIDE];
-        w[4 * c + 0] |= v.x & m;
-        w[4 * c + 1] |= v.y & m;
-        w[4 * c + 2] |= v.z & m;
-        w[4 * c + 3] |= v.w & m;
+    for (int c = 0; c < HALF; c++) buf[0][c] = col[c * STRIDE];
+#pragma unroll
+    for (int hq = 0; hq < 2 * VB_ENTRIES; hq++) {
+      if (hq + 1 < 2 * VB_ENTRIES) {
+#pragma unroll
+        for (int c = 0; c < HALF; c++) buf[(hq + 1) & 1][c] = col[(size_t)((hq + 1) * HALF + c) * STRIDE];
+      }
+      const uint32_t m = ((uint32_t)(hq / 2 + 1) == mag) ? 0xffffffffu : 0u;
+      const int c0 = (hq & 1) * HALF;
+#pragma unroll
+      for (int c = 0; c < HALF; c++) {
+        const uint4 v = buf[hq & 1][c];
+        w[4 * (c0 + c) + 0] |= v.x & m;
+        w[4 * (c0 + c) + 1] |= v.y & m;
+        w[4 * (c0 + c) + 2] |= v.z & m;
+        w[4 * (c0 + c) + 3] |= v.w & m;
       }
     }
   } else {
@@ -460,7 +477,7 @@ CAPY_HD void vb_add(PtExt& r, const PtCached& q, bool want_t) {
 }
 
 // r = [k]P (+ addend).  On entry r = P (extended, tight); `load_addend(PtExt&)` is only called when has_addend.
-// In a CUDA block every thread must call this (block barriers keep the warps on one instruction stream).
+// (With CAPY_VB_SYNC every thread of a CUDA block must call this: block barriers then keep the warps on one instruction stream.)
 template <int STRIDE, class LoadAddend>
 CAPY_HD void pt_var_base_mul(PtExt& r, const Sc& k, uint4* col, bool CONSTANT_TIME, bool has_addend, LoadAddend&& load_addend) {
   uint32_t K[15];

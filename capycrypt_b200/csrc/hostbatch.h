@@ -139,6 +139,7 @@ inline int for_each_device(capy_ctx* ctx, const std::vector<Range>& shards, F&& 
     DeviceCtx& dc = ctx->devs[0];
     std::lock_guard<std::mutex> lk(*dc.mu);
     DeviceGuard g(dc.dev);
+    HostOffScope hs(dc);
     return fn(dc, shards[0]);
   }
   std::vector<int> rcs(shards.size(), CAPY_OK);
@@ -150,6 +151,7 @@ inline int for_each_device(capy_ctx* ctx, const std::vector<Range>& shards, F&& 
     dc.worker->post([&, k] {
       {
         std::lock_guard<std::mutex> lk(*ctx->devs[k].mu);
+        HostOffScope hs(ctx->devs[k]);
         rcs[k] = fn(ctx->devs[k], shards[k]);
       }
       std::lock_guard<std::mutex> lk(m);
@@ -182,6 +184,7 @@ inline int stage_packed(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t st, int slot_
   CAPY_CUDA(ctx, cudaMemcpyAsync(d_off, off + i0, (size_t)(i1 - i0 + 1) * 8, cudaMemcpyHostToDevice, st));
   out->d_base = reinterpret_cast<const uint8_t*>(reinterpret_cast<uintptr_t>(d_data) - (uintptr_t)a0);
   out->d_off = d_off;
+  host_off_register(dc, d_off, off + i0, i1 - i0 + 1);  // plan_ragged plans from the host copy: no device round trip
   return CAPY_OK;
 }
 

@@ -84,6 +84,15 @@ struct DeviceCtx {
   Scratch scratch[kNumScratch];
   std::map<std::string, PrefixState> prefix_cache;
   std::vector<PlanEntry> plans;
+  // host copies of the offsets arrays a host entry point has staged into device scratch (stage_packed), keyed by the
+  // device address: plan_ragged reads the lengths from the host copy instead of fetching the histogram summary from the
+  // device (no stream synchronisation inside a host-buffer call).  Valid only while that host call runs (HostOffScope).
+  struct HostOff {
+    const uint64_t* d_off;
+    const uint64_t* h_off;
+    uint64_t count;  // entries (items + 1)
+  };
+  std::vector<HostOff> host_offs;
   uint64_t use_clock = 0;
   Ed448Tables* ed = nullptr;
   int sm_count = 0;
@@ -124,6 +133,27 @@ int cuda_fail(capy_ctx* ctx, cudaError_t e, const char* what);
 
 // returns nullptr on OOM
 void* scratch_get(DeviceCtx& dc, int slot, size_t bytes);
+
+// the host arrays registered in dc.host_offs belong to the caller of ONE host entry point: forget them when it returns
+struct HostOffScope {
+  DeviceCtx& dc;
+  explicit HostOffScope(DeviceCtx& d) : dc(d) { dc.host_offs.clear(); }
+  ~HostOffScope() { dc.host_offs.clear(); }
+};
+inline void host_off_register(DeviceCtx& dc, const uint64_t* d_off, const uint64_t* h_off, uint64_t count) {
+  for (auto& e : dc.host_offs)
+    if (e.d_off == d_off) {
+      e.h_off = h_off;
+      e.count = count;
+      return;
+    }
+  dc.host_offs.push_back({d_off, h_off, count});
+}
+inline const uint64_t* host_off_find(const DeviceCtx& dc, const uint64_t* d_off, uint64_t n) {
+  for (const auto& e : dc.host_offs)
+    if (e.d_off == d_off && e.count >= n + 1) return e.h_off;
+  return nullptr;
+}
 
 inline bool valid_secparam(int d) { return d == 224 || d == 256 || d == 384 || d == 512; }
 inline uint32_t bytepad_value(int d) { return d == 224 ? 172u : d == 256 ? 168u : d == 384 ? 152u : 136u; }  // lib.rs:137-144

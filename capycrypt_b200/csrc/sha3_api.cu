@@ -160,6 +160,7 @@ static inline unsigned grid_for(uint64_t n, unsigned block) { return (unsigned)(
 // ------------------------------------------------------------------------------------------------
 // 16 384 bins of one block each; longer messages (>= 1.1 MB at the SHA3-512 rate) share the last bin
 constexpr uint32_t kLenBins = 1u << 14;
+constexpr uint64_t kHostPlanMaxItems = 1ull << 18;  // plan_ragged: largest batch whose histogram is taken on the host
 
 __device__ __forceinline__ uint32_t len_bin(const uint64_t* off, uint64_t i, uint32_t stride_bytes) {
   const uint64_t blocks = (off[i + 1] - off[i]) / stride_bytes;
@@ -340,7 +341,36 @@ static int plan_ragged(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t st, const uint
                        uint32_t stride_bytes, LaunchPlan* plan, bool allow_pair = true, int force_c = 0) {
   *plan = LaunchPlan();
   if (n < 1 || n > 0xffffffffull) return CAPY_OK;
-  const bool cached = ctx->plan_cache.load() != 0 && force_c == 0;
+  // Host-buffer entry points: the offsets were staged from a host array that is still alive (stage_packed registers it).
+  // The lengths are read there, so nothing comes back from the device and the chunk pipeline of the host call never
+  // waits for a stream.  Uniform lengths (the bulk case: fixed-size records) need no device work at all.
+  const uint64_t* h_off = host_off_find(dc, d_off, n);
+  std::vector<uint32_t> h_cnt;  // host histogram (non-uniform batches up to kHostPlanMaxItems)
+  uint64_t h_total = 0;
+  uint32_t h_max = 0, h_bins = 0;
+  if (h_off) {
+    const uint64_t len0 = h_off[1] - h_off[0];
+    bool uniform = true;
+    for (uint64_t i = 1; i < n && uniform; i++) uniform = (h_off[i + 1] - h_off[i]) == len0;
+    if (uniform) return CAPY_OK;  // nothing to order, no chain stands out
+    if (n > kHostPlanMaxItems) {
+      h_off = nullptr;  // a histogram of millions of items is cheaper on the device, round trip included
+    } else {
+      h_cnt.assign(kLenBins, 0);
+      const double inv = 1.0 / (double)stride_bytes;
+      for (uint64_t i = 0; i < n; i++) {
+        const uint64_t len = h_off[i + 1] - h_off[i];
+        uint64_t q = (uint64_t)((double)len * inv);  // len / stride_bytes without a 64-bit division per item
+        if (q * stride_bytes > len) q--;
+        else if ((q + 1) * stride_bytes <= len) q++;
+        const uint32_t b = q < kLenBins - 1 ? (uint32_t)q : kLenBins - 1;
+        if (h_cnt[b]++ == 0) h_bins++;
+        if (b > h_max) h_max = b;
+        h_total += (uint64_t)b + 1;
+      }
+    }
+  }
+  const bool cached = ctx->plan_cache.load() != 0 && force_c == 0 && !h_off;
   if (cached) {
     for (PlanEntry& e : dc.plans)
       if (e.off == d_off && e.n == n && e.unit == stride_bytes && e.allow_pair == allow_pair) {
@@ -382,9 +412,11 @@ static int plan_ragged(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t st, const uint
   len_hist_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_off, n, stride_bytes, hist);
   len_scan_kernel<<<1, 1024, 0, st>>>(hist, summary);
   ctx->launches += 2;
-  uint32_t h_sum[4];
-  PLAN_CUDA(cudaMemcpyAsync(h_sum, summary, sizeof h_sum, cudaMemcpyDeviceToHost, st));
-  PLAN_CUDA(cudaStreamSynchronize(st));
+  uint32_t h_sum[4] = {(uint32_t)h_total, (uint32_t)(h_total >> 32), h_max, h_bins};
+  if (!h_off) {
+    PLAN_CUDA(cudaMemcpyAsync(h_sum, summary, sizeof h_sum, cudaMemcpyDeviceToHost, st));
+    PLAN_CUDA(cudaStreamSynchronize(st));
+  }
   const uint64_t total_blocks = (uint64_t)h_sum[0] | ((uint64_t)h_sum[1] << 32);
   const uint32_t max_blocks = h_sum[2] + 1, bins = h_sum[3];
   // time in units of one thread-per-state permutation on one scheduler: all work spread over every scheduler
@@ -393,8 +425,16 @@ static int plan_ragged(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t st, const uint
   // Chain-bound batch: the longest items go to the warp-per-item and the two-threads-per-item tiers
   if (allow_pair && max_blocks > 64 && (double)max_blocks > 1.05 * ideal) {
     std::vector<uint32_t> cum(kLenBins);  // after the scan hist[k] = number of items in bins > k
-    PLAN_CUDA(cudaMemcpyAsync(cum.data(), hist, (size_t)kLenBins * 4, cudaMemcpyDeviceToHost, st));
-    PLAN_CUDA(cudaStreamSynchronize(st));
+    if (h_off) {
+      uint32_t above = 0;
+      for (uint32_t k = kLenBins; k-- > 0;) {
+        cum[k] = above;
+        above += h_cnt[k];
+      }
+    } else {
+      PLAN_CUDA(cudaMemcpyAsync(cum.data(), hist, (size_t)kLenBins * 4, cudaMemcpyDeviceToHost, st));
+      PLAN_CUDA(cudaStreamSynchronize(st));
+    }
     plan_tiers(cum, n, max_blocks, (double)total_blocks, dc.sm_count, plan->warp_items, &plan->pair_items, force_c);
   }
   if (bins > 1) {  // (uniform lengths: nothing to order)
@@ -921,6 +961,7 @@ int capy_sha3_batch(capy_ctx* ctx, int d_bits, const uint8_t* data, const uint64
         }
         loc[j] = at;
         CAPY_CUDA(ctx, cudaMemcpyAsync(d_off, loc.data(), (size_t)(sh.items + 1) * 8, cudaMemcpyHostToDevice, st));
+        host_off_register(dc, d_off, loc.data(), sh.items + 1);
         int rc = launch_sha3(ctx, dc, st, d_bits, d_data, d_off, 0, 0, sh.items, d_out, flags);
         if (rc) return rc;
         j = 0;

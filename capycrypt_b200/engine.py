@@ -35,6 +35,17 @@ def _hp(a: np.ndarray | None):
 _DUMMY = np.zeros(16, np.uint8)
 
 
+def _out(out, shape, what: str) -> np.ndarray:
+    """result buffer: a fresh (pageable) array, or the caller's -- e.g. pinned memory from Engine.pinned(), which the
+    device-to-host copy then reaches at link speed."""
+    if out is None:
+        return np.zeros(shape, dtype=np.uint8)
+    if not (isinstance(out, np.ndarray) and out.dtype == np.uint8 and out.flags.c_contiguous and out.flags.writeable):
+        raise ValueError(f"{what}: out must be a writable C-contiguous uint8 array")
+    _need(out.reshape(-1), int(np.prod(shape)), what)
+    return out
+
+
 def _need(buf: np.ndarray, nbytes: int, what: str) -> None:
     """The C side trusts (pointer, n): refuse a buffer shorter than n * stride here instead of letting the
     library read past a numpy allocation."""
@@ -135,10 +146,10 @@ class Engine:
     # =================================================================================
     # host-buffer API (blocking)
     # =================================================================================
-    def sha3(self, data, off, d: int) -> np.ndarray:
+    def sha3(self, data, off, d: int, out: np.ndarray | None = None) -> np.ndarray:
         data, off = _u8(data), _u64(off)
         n = _need_packed(data, off, "sha3 messages")
-        out = np.zeros((n, max(d // 8, 0) if d in (224, 256, 384, 512) else 1), dtype=np.uint8)
+        out = _out(out, (n, max(d // 8, 0) if d in (224, 256, 384, 512) else 1), "sha3 digests")
         self._check(self.lib.capy_sha3_batch(self._ctx, d, _hp(data), _hp(off), n, _hp(out), 0))
         return out
 
@@ -153,29 +164,30 @@ class Engine:
         self._check(self.lib.capy_sha3_batch_fixed(self._ctx, d, _hp(data), msg_len, stride, n, _hp(out), 0))
         return out
 
-    def cshake(self, data, off, out_bits: int, fn: bytes, custom: bytes, d: int) -> np.ndarray:
+    def cshake(self, data, off, out_bits: int, fn: bytes, custom: bytes, d: int, out: np.ndarray | None = None) -> np.ndarray:
         data, off = _u8(data), _u64(off)
         n = _need_packed(data, off, "cshake messages")
-        out = np.zeros((n, out_bits // 8), dtype=np.uint8)
+        out = _out(out, (n, out_bits // 8), "cshake output")
         fn_a, cs_a = _u8(fn), _u8(custom)
         self._check(self.lib.capy_cshake_batch(self._ctx, d, _hp(data), _hp(off), n, _hp(fn_a), len(fn_a), _hp(cs_a),
                                                len(cs_a), out_bits, _hp(out)))
         return out
 
-    def kmac_xof(self, keys, key_off, data, off, out_bits: int, custom: bytes, d: int, out_off=None) -> np.ndarray:
+    def kmac_xof(self, keys, key_off, data, off, out_bits: int, custom: bytes, d: int, out_off=None,
+                 out: np.ndarray | None = None) -> np.ndarray:
         keys, key_off, data, off = _u8(keys), _u64(key_off), _u8(data), _u64(off)
         n = _need_packed(data, off, "kmac messages")
         if _need_packed(keys, key_off, "kmac keys") != n:
             raise ValueError("kmac: keys and messages differ in count")
         cs_a = _u8(custom)
         if out_off is None:
-            out = np.zeros((n, out_bits // 8), dtype=np.uint8)
+            out = _out(out, (n, out_bits // 8), "kmac output")
             oo = None
         else:
             out_off = _u64(out_off)
             if out_off.size != n + 1 or bool(np.any(out_off[1:] < out_off[:-1])):
                 raise ValueError("kmac: out_off needs n + 1 non-decreasing entries")
-            out = np.zeros(int(out_off[-1]), dtype=np.uint8)
+            out = _out(out, (int(out_off[-1]),), "kmac output")
             oo = _hp(out_off)
         self._check(self.lib.capy_kmac_xof_batch(self._ctx, d, _hp(keys), _hp(key_off), _hp(data), _hp(off), n,
                                                  _hp(cs_a), len(cs_a), out_bits, oo, _hp(out)))
@@ -204,30 +216,31 @@ class Engine:
                          allow=(B.ERR_BAD_POINT,))
         return rc, out
 
-    def ed448_keygen(self, pws, pw_off, d: int) -> np.ndarray:
+    def ed448_keygen(self, pws, pw_off, d: int, out: np.ndarray | None = None) -> np.ndarray:
         pws, pw_off = _u8(pws), _u64(pw_off)
         n = _need_packed(pws, pw_off, "keygen passwords")
-        out = np.zeros((n, 112), dtype=np.uint8)
+        out = _out(out, (n, 112), "keygen output")
         self._check(self.lib.capy_ed448_keygen_batch(self._ctx, d, _hp(pws), _hp(pw_off), n, _hp(out)))
         return out
 
-    def ed448_sign(self, pws, pw_off, msgs, msg_off, d: int) -> tuple[np.ndarray, np.ndarray]:
+    def ed448_sign(self, pws, pw_off, msgs, msg_off, d: int, h_out: np.ndarray | None = None,
+                   z_out: np.ndarray | None = None) -> tuple[np.ndarray, np.ndarray]:
         pws, pw_off, msgs, msg_off = _u8(pws), _u64(pw_off), _u8(msgs), _u64(msg_off)
         n = _need_packed(pws, pw_off, "sign passwords")
         if _need_packed(msgs, msg_off, "sign messages") != n:
             raise ValueError("sign: passwords and messages differ in count")
-        h = np.zeros((n, 56), dtype=np.uint8)
-        z = np.zeros((n, 56), dtype=np.uint8)
+        h = _out(h_out, (n, 56), "sign h")
+        z = _out(z_out, (n, 56), "sign z")
         self._check(self.lib.capy_ed448_sign_batch(self._ctx, d, _hp(pws), _hp(pw_off), _hp(msgs), _hp(msg_off), n,
                                                    _hp(h), _hp(z)))
         return h, z
 
-    def ed448_verify(self, pub_xy112, msgs, msg_off, h56, z_be56, d: int) -> tuple[int, np.ndarray]:
+    def ed448_verify(self, pub_xy112, msgs, msg_off, h56, z_be56, d: int, ok_out: np.ndarray | None = None) -> tuple[int, np.ndarray]:
         pub, msgs, msg_off, h, z = _u8(pub_xy112), _u8(msgs), _u64(msg_off), _u8(h56), _u8(z_be56)
         n = _need_packed(msgs, msg_off, "verify messages")
         if len(pub) != n * 112 or len(h) != n * 56 or len(z) != n * 56:
             raise ValueError(f"verify: pub/h/z hold {len(pub)}/{len(h)}/{len(z)} bytes, need {n} x 112/56/56")
-        ok = np.zeros(n, dtype=np.uint8)
+        ok = _out(ok_out, (n,), "verify flags")
         rc = self._check(self.lib.capy_ed448_verify_batch(self._ctx, d, _hp(pub), _hp(msgs), _hp(msg_off), _hp(h),
                                                           _hp(z), n, _hp(ok)), allow=(B.ERR_BAD_POINT,))
         return rc, ok

@@ -127,3 +127,36 @@ def test_copy_probe_reports_a_link_time(engine):
     assert 0.01 < ms < 50.0  # 8 MiB in + 4 MiB out: between 240 GB/s and 0.25 GB/s
     with pytest.raises(Exception):
         engine.copy_probe(h_in, h_out, reps=0)
+
+
+def test_host_calls_plan_from_the_host_offsets(engine, oracle):
+    """Host-buffer entry points read the lengths from the caller's offsets array (no histogram round trip): a uniform
+    batch is ONE launch, a chain-bound ragged batch still gets its tiers and the longest-first order, same digests."""
+    rnd = np.random.default_rng(21)
+    n = 4096
+    data = rnd.integers(0, 256, size=n * 200, dtype=np.uint8)
+    off = (np.arange(n + 1, dtype=np.uint64) * 200)
+    l0 = engine.launch_count
+    got = engine.sha3(data, off, 512)
+    assert engine.launch_count - l0 == 1  # uniform lengths through the ragged entry point: the sponge launch only
+    assert np.array_equal(got, oracle.sha3_batch(data, off, 512, threads=0))
+    keys = rnd.integers(0, 256, size=n * 32, dtype=np.uint8)
+    koff = np.arange(n + 1, dtype=np.uint64) * 32
+    l0 = engine.launch_count
+    tags = engine.kmac_xof(keys, koff, data, off, 512, b"tag", 512, out=engine.pinned(n * 64).reshape(n, 64))
+    assert engine.launch_count - l0 <= 2  # (+ the prefix state when "tag" is new to the cache)
+    assert np.array_equal(tags[:64], oracle.kmac_xof_batch(keys[: 64 * 32], koff[:65], data[: 64 * 200], off[:65], 512, b"tag", 512))
+    # chain-bound: a few long messages among short ones
+    lens = np.concatenate([rnd.integers(200_000, 500_000, size=12), rnd.integers(0, 2000, size=3000)])
+    rnd.shuffle(lens)
+    off2 = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    data2 = rnd.integers(0, 256, size=int(off2[-1]), dtype=np.uint8)
+    l0 = engine.launch_count
+    got2 = engine.sha3(data2, off2, 512)
+    assert engine.launch_count - l0 == 4  # histogram, scan, scatter, one tiered sponge launch -- and no D2H of the plan
+    assert np.array_equal(got2, oracle.sha3_batch(data2, off2, 512, threads=0))
+    # the same batch through the device-pointer entry point (plan fetched from the device) gives the same bytes
+    t_out = torch.zeros(len(lens) * 64, dtype=torch.uint8, device="cuda")
+    engine.sha3_dev(torch.from_numpy(data2).cuda(), torch.from_numpy(off2.astype(np.int64)).cuda(), 512, t_out)
+    torch.cuda.synchronize()
+    assert np.array_equal(t_out.cpu().numpy().reshape(-1, 64), got2)
