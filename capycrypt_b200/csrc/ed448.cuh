@@ -130,9 +130,12 @@ CAPY_HD bool pt_from_affine(PtExt& p, const Fe& x, const Fe& y) {
 // so this is exact).  On E' (a = -1) a mixed addition with a precomputed Niels entry (y - x, y + x, 2 d' x y)
 // costs 7 M instead of 8 M on E.  Signed radix-32 digits: 90 windows x 16 entries = 270 KB table, 90 mixed
 // additions and no doubling per scalar multiplication.
-constexpr int FB_WBITS = 5;
-constexpr int FB_WINDOWS = 90;
-constexpr int FB_ENTRIES = 16;
+#ifndef CAPY_FB_WBITS
+#define CAPY_FB_WBITS 5  // measured: 4 / 5 / 6 bits -> see profiles/README.md round 2 (scan cost against additions)
+#endif
+constexpr int FB_WBITS = CAPY_FB_WBITS;
+constexpr int FB_WINDOWS = (447 + FB_WBITS - 1) / FB_WBITS;  // kq < r < 2^446, one more bit for the signed recoding
+constexpr int FB_ENTRIES = 1 << (FB_WBITS - 1);
 constexpr int FB_ENTRY_WORDS = 48;  // ymx | ypx | td2, 16 canonical limbs each
 constexpr uint32_t EDW_2D_TW_ABS = 2u * 39082u;  // 2 d' = -78164
 

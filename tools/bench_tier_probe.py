@@ -25,6 +25,7 @@ def mixed(total):
         c = np.exp(rs.uniform(np.log(64), np.log(1 << 20), size=8192)).astype(np.int64); lens.append(c); acc += int(c.sum())
     lens = np.concatenate(lens); return lens[: int(np.searchsorted(np.cumsum(lens), total)) + 1]
 cases = [("mixed 16 GiB", mixed(16 << 30)), ("mixed 8 GiB", mixed(8 << 30)), ("mixed 4 GiB", mixed(4 << 30)), ("mixed 2 GiB", mixed(2 << 30)),
+         ("4096 x 1 MiB (pair tier only: the warp-tier blocks would not all be resident)", np.full(4096, 1 << 20)),
          ("1024 x 1 MiB", np.full(1024, 1 << 20)), ("64 x 1 MiB", np.full(64, 1 << 20)), ("1 x 4 MiB", np.array([4 << 20]))]
 for name, lens in cases:
     lens = np.asarray(lens, dtype=np.int64)
