@@ -160,8 +160,21 @@ enum {
   SL_H_IN0 = 36  // 36.. host staging
 };
 
-#define CAPY_SCRATCH(var, type, slot, bytes)                \
-  type* var = (type*)scratch_get(dc, (slot), (bytes));      \
+// The pipelines below keep their intermediates in fixed scratch slots.  A host entry point runs several chunks at once on
+// the device's internal streams, so every internal stream has its own copy of the slots 24..54 (stream 0: the slots
+// themselves, streams 1 and 2: shadow ranges behind the AE slots); a caller's stream (the _dev entry points) uses set 0.
+// Slot 55 (the per-SM table slabs of var_base_kernel) is shared: an SM runs one var_base block at a time.
+constexpr int kEdShadowBase = 80, kEdShadowStride = 32;
+static_assert(kEdShadowBase + (kNumStreams - 1) * kEdShadowStride <= kNumScratch, "scratch slots of the stream copies");
+static inline int ed_stream_index(const DeviceCtx& dc, cudaStream_t st) {
+  for (int k = 1; k < kNumStreams; k++)
+    if (dc.streams[k] == st) return k;
+  return 0;
+}
+static inline int ed_slot(int slot, int ss) { return ss == 0 ? slot : kEdShadowBase + (ss - 1) * kEdShadowStride + (slot - 24); }
+
+#define CAPY_SCRATCH(var, type, slot, bytes)                                                    \
+  type* var = (type*)scratch_get(dc, ed_slot((slot), ed_stream_index(dc, st)), (bytes));        \
   if (!var) return CAPY_ERR_OOM;
 
 // ---- device pipelines (async on `st`) ----------------------------------------------------------------
@@ -312,9 +325,36 @@ static int h2d(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t st, int slot, const vo
   return CAPY_OK;
 }
 
-static int read_flag(capy_ctx* ctx, cudaStream_t st, int* d_flag, int* h_flag) {
-  CAPY_CUDA(ctx, cudaMemcpyAsync(h_flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
-  CAPY_CUDA(ctx, cudaStreamSynchronize(st));
+// Runs `body(stream, slot set, chunk, d_flag)` for the chunks of one device's shard, rotating over the internal streams
+// (body enqueues the copies in, the pipeline and the copies out of its chunk and does not wait), then waits for the
+// streams.  flag_out (optional): the OR of what the chunks left in their stream's "bad point" flag.
+// Chunks of at least 2^18 items: the pipelines contain latency-bound steps (the batch inversion of to_affine_kernel runs
+// 16 items per thread, ~0.3 ms however few) that smaller chunks would repeat too often -- measured: four chunks of 2^16
+// through capy_ed448_fixed_base_batch 7.05 ms against 6.9 ms unchunked, although the copies (0.8 ms) were hidden.
+static size_t ed_chunk_count(uint64_t items) { return items < (1ull << 19) ? 1 : (size_t)std::min<uint64_t>(8, items >> 18); }
+
+template <class F>
+static int ed_host_chunks(capy_ctx* ctx, DeviceCtx& dc, Range sh, int* flag_out, F&& body) {
+  auto chunks = split_items(nullptr, 1, sh.i0, sh.i1, ed_chunk_count(sh.i1 - sh.i0), 0);
+  const int used = (int)std::min<size_t>(chunks.size(), kNumStreams);
+  int* d_flags[kNumStreams] = {};
+  for (int s = 0; s < used; s++) {
+    d_flags[s] = (int*)scratch_get(dc, ed_slot(SL_FLAG, s), sizeof(int));
+    if (!d_flags[s]) return CAPY_ERR_OOM;
+    CAPY_CUDA(ctx, cudaMemsetAsync(d_flags[s], 0, sizeof(int), dc.streams[s]));
+  }
+  for (size_t c = 0; c < chunks.size(); c++) {
+    const int s = (int)(c % kNumStreams);
+    int rc = body(dc.streams[s], s, chunks[c], d_flags[s]);
+    if (rc) return rc;
+  }
+  int h_flags[kNumStreams] = {};
+  for (int s = 0; s < used; s++) {
+    if (flag_out) CAPY_CUDA(ctx, cudaMemcpyAsync(&h_flags[s], d_flags[s], sizeof(int), cudaMemcpyDeviceToHost, dc.streams[s]));
+    CAPY_CUDA(ctx, cudaStreamSynchronize(dc.streams[s]));
+  }
+  if (flag_out)
+    for (int s = 0; s < used; s++) *flag_out |= h_flags[s];
   return CAPY_OK;
 }
 
@@ -368,24 +408,26 @@ int capy_ed448_verify_batch_dev(capy_ctx* ctx, int dev_index, void* stream, int 
   return dev_verify(ctx, dc, st, d_bits, d_pub_xy112, d_msgs, d_msg_off, d_h56, d_z_be56, n, d_ok, d_bad_flag);
 }
 
-// ---- host-buffer entry points: shard across the ctx devices by item count, one stream per device ----
+// ---- host-buffer entry points: shard across the ctx devices by item count; inside a device the shard is cut into chunks
+// that rotate over the device's streams (own scratch slots per stream, ed_slot), so the copies of one chunk run under the
+// kernels of its neighbours ----
 int capy_ed448_fixed_base_batch(capy_ctx* ctx, const uint8_t* scalars_be56, uint64_t n, uint8_t* out_xy112) {
   if (!ctx || (n && (!scalars_be56 || !out_xy112))) return CAPY_ERR_BAD_ARG;
   if (n == 0) return CAPY_OK;
   auto shards = split_items(nullptr, 1, 0, n, ctx->devs.size(), 0);
   return for_each_device(ctx, shards, [&](DeviceCtx& dc, Range sh) -> int {
-    cudaStream_t st = dc.streams[0];
-    const uint64_t cnt = sh.i1 - sh.i0;
-    uint8_t *d_sc = nullptr, *d_out = nullptr;
-    int rc = h2d(ctx, dc, st, SL_H_IN0, scalars_be56 + 56 * sh.i0, cnt * 56, &d_sc);
-    if (rc) return rc;
-    d_out = (uint8_t*)scratch_get(dc, SL_H_IN0 + 1, cnt * 112);
-    if (!d_out) return CAPY_ERR_OOM;
-    rc = dev_fixed_base(ctx, dc, st, d_sc, cnt, d_out);
-    if (rc) return rc;
-    CAPY_CUDA(ctx, cudaMemcpyAsync(out_xy112 + 112 * sh.i0, d_out, cnt * 112, cudaMemcpyDeviceToHost, st));
-    CAPY_CUDA(ctx, cudaStreamSynchronize(st));
-    return CAPY_OK;
+    return ed_host_chunks(ctx, dc, sh, nullptr, [&](cudaStream_t st, int ss, Range ch, int*) -> int {
+      const uint64_t cnt = ch.i1 - ch.i0;
+      uint8_t *d_sc = nullptr, *d_out = nullptr;
+      int rc = h2d(ctx, dc, st, ed_slot(SL_H_IN0, ss), scalars_be56 + 56 * ch.i0, cnt * 56, &d_sc);
+      if (rc) return rc;
+      d_out = (uint8_t*)scratch_get(dc, ed_slot(SL_H_IN0 + 1, ss), cnt * 112);
+      if (!d_out) return CAPY_ERR_OOM;
+      rc = dev_fixed_base(ctx, dc, st, d_sc, cnt, d_out);
+      if (rc) return rc;
+      CAPY_CUDA(ctx, cudaMemcpyAsync(out_xy112 + 112 * ch.i0, d_out, cnt * 112, cudaMemcpyDeviceToHost, st));
+      return CAPY_OK;
+    });
   });
 }
 
@@ -396,21 +438,20 @@ int capy_ed448_var_base_batch(capy_ctx* ctx, const uint8_t* scalars_be56, const 
   std::vector<int> flags(ctx->devs.size(), 0);
   auto shards = split_items(nullptr, 1, 0, n, ctx->devs.size(), 0);
   int rc = for_each_device(ctx, shards, [&](DeviceCtx& dc, Range sh) -> int {
-    cudaStream_t st = dc.streams[0];
-    const uint64_t cnt = sh.i1 - sh.i0;
-    uint8_t *d_sc = nullptr, *d_pt = nullptr;
-    int rc = h2d(ctx, dc, st, SL_H_IN0, scalars_be56 + 56 * sh.i0, cnt * 56, &d_sc);
-    if (rc) return rc;
-    rc = h2d(ctx, dc, st, SL_H_IN0 + 1, points_xy112 + 112 * sh.i0, cnt * 112, &d_pt);
-    if (rc) return rc;
-    uint8_t* d_out = (uint8_t*)scratch_get(dc, SL_H_IN0 + 2, cnt * 112);
-    int* d_flag = (int*)scratch_get(dc, SL_FLAG, sizeof(int));
-    if (!d_out || !d_flag) return CAPY_ERR_OOM;
-    CAPY_CUDA(ctx, cudaMemsetAsync(d_flag, 0, sizeof(int), st));
-    rc = dev_var_base(ctx, dc, st, d_sc, d_pt, cnt, d_out, d_flag);
-    if (rc) return rc;
-    CAPY_CUDA(ctx, cudaMemcpyAsync(out_xy112 + 112 * sh.i0, d_out, cnt * 112, cudaMemcpyDeviceToHost, st));
-    return read_flag(ctx, st, d_flag, &flags[dc.index]);
+    return ed_host_chunks(ctx, dc, sh, &flags[dc.index], [&](cudaStream_t st, int ss, Range ch, int* d_flag) -> int {
+      const uint64_t cnt = ch.i1 - ch.i0;
+      uint8_t *d_sc = nullptr, *d_pt = nullptr;
+      int rc = h2d(ctx, dc, st, ed_slot(SL_H_IN0, ss), scalars_be56 + 56 * ch.i0, cnt * 56, &d_sc);
+      if (rc) return rc;
+      rc = h2d(ctx, dc, st, ed_slot(SL_H_IN0 + 1, ss), points_xy112 + 112 * ch.i0, cnt * 112, &d_pt);
+      if (rc) return rc;
+      uint8_t* d_out = (uint8_t*)scratch_get(dc, ed_slot(SL_H_IN0 + 2, ss), cnt * 112);
+      if (!d_out) return CAPY_ERR_OOM;
+      rc = dev_var_base(ctx, dc, st, d_sc, d_pt, cnt, d_out, d_flag);
+      if (rc) return rc;
+      CAPY_CUDA(ctx, cudaMemcpyAsync(out_xy112 + 112 * ch.i0, d_out, cnt * 112, cudaMemcpyDeviceToHost, st));
+      return CAPY_OK;
+    });
   });
   if (rc) return rc;
   for (int f : flags)
@@ -425,18 +466,18 @@ int capy_ed448_keygen_batch(capy_ctx* ctx, int d_bits, const uint8_t* pws, const
   if (n == 0) return CAPY_OK;
   auto shards = split_items(nullptr, 1, 0, n, ctx->devs.size(), 0);
   return for_each_device(ctx, shards, [&](DeviceCtx& dc, Range sh) -> int {
-    cudaStream_t st = dc.streams[0];
-    const uint64_t cnt = sh.i1 - sh.i0;
-    StagedPacked sp;
-    int rc = stage_packed(ctx, dc, st, SL_H_IN0, SL_H_IN0 + 1, pws, pw_off, sh.i0, sh.i1, &sp);
-    if (rc) return rc;
-    uint8_t* d_out = (uint8_t*)scratch_get(dc, SL_H_IN0 + 2, cnt * 112);
-    if (!d_out) return CAPY_ERR_OOM;
-    rc = dev_keygen(ctx, dc, st, d_bits, sp.d_base, sp.d_off, cnt, d_out);
-    if (rc) return rc;
-    CAPY_CUDA(ctx, cudaMemcpyAsync(out_xy112 + 112 * sh.i0, d_out, cnt * 112, cudaMemcpyDeviceToHost, st));
-    CAPY_CUDA(ctx, cudaStreamSynchronize(st));
-    return CAPY_OK;
+    return ed_host_chunks(ctx, dc, sh, nullptr, [&](cudaStream_t st, int ss, Range ch, int*) -> int {
+      const uint64_t cnt = ch.i1 - ch.i0;
+      StagedPacked sp;
+      int rc = stage_packed(ctx, dc, st, ed_slot(SL_H_IN0, ss), ed_slot(SL_H_IN0 + 1, ss), pws, pw_off, ch.i0, ch.i1, &sp);
+      if (rc) return rc;
+      uint8_t* d_out = (uint8_t*)scratch_get(dc, ed_slot(SL_H_IN0 + 2, ss), cnt * 112);
+      if (!d_out) return CAPY_ERR_OOM;
+      rc = dev_keygen(ctx, dc, st, d_bits, sp.d_base, sp.d_off, cnt, d_out);
+      if (rc) return rc;
+      CAPY_CUDA(ctx, cudaMemcpyAsync(out_xy112 + 112 * ch.i0, d_out, cnt * 112, cudaMemcpyDeviceToHost, st));
+      return CAPY_OK;
+    });
   });
 }
 
@@ -447,22 +488,22 @@ int capy_ed448_sign_batch(capy_ctx* ctx, int d_bits, const uint8_t* pws, const u
   if (n == 0) return CAPY_OK;
   auto shards = split_items(msg_off, 0, 0, n, ctx->devs.size(), 4096);
   return for_each_device(ctx, shards, [&](DeviceCtx& dc, Range sh) -> int {
-    cudaStream_t st = dc.streams[0];
-    const uint64_t cnt = sh.i1 - sh.i0;
-    StagedPacked sp, sm;
-    int rc = stage_packed(ctx, dc, st, SL_H_IN0, SL_H_IN0 + 1, pws, pw_off, sh.i0, sh.i1, &sp);
-    if (rc) return rc;
-    rc = stage_packed(ctx, dc, st, SL_H_IN0 + 2, SL_H_IN0 + 3, msgs, msg_off, sh.i0, sh.i1, &sm);
-    if (rc) return rc;
-    uint8_t* d_h = (uint8_t*)scratch_get(dc, SL_H_IN0 + 4, cnt * 56);
-    uint8_t* d_z = (uint8_t*)scratch_get(dc, SL_H_IN0 + 5, cnt * 56);
-    if (!d_h || !d_z) return CAPY_ERR_OOM;
-    rc = dev_sign(ctx, dc, st, d_bits, sp.d_base, sp.d_off, sm.d_base, sm.d_off, cnt, d_h, d_z);
-    if (rc) return rc;
-    CAPY_CUDA(ctx, cudaMemcpyAsync(h56 + 56 * sh.i0, d_h, cnt * 56, cudaMemcpyDeviceToHost, st));
-    CAPY_CUDA(ctx, cudaMemcpyAsync(z_be56 + 56 * sh.i0, d_z, cnt * 56, cudaMemcpyDeviceToHost, st));
-    CAPY_CUDA(ctx, cudaStreamSynchronize(st));
-    return CAPY_OK;
+    return ed_host_chunks(ctx, dc, sh, nullptr, [&](cudaStream_t st, int ss, Range ch, int*) -> int {
+      const uint64_t cnt = ch.i1 - ch.i0;
+      StagedPacked sp, sm;
+      int rc = stage_packed(ctx, dc, st, ed_slot(SL_H_IN0, ss), ed_slot(SL_H_IN0 + 1, ss), pws, pw_off, ch.i0, ch.i1, &sp);
+      if (rc) return rc;
+      rc = stage_packed(ctx, dc, st, ed_slot(SL_H_IN0 + 2, ss), ed_slot(SL_H_IN0 + 3, ss), msgs, msg_off, ch.i0, ch.i1, &sm);
+      if (rc) return rc;
+      uint8_t* d_h = (uint8_t*)scratch_get(dc, ed_slot(SL_H_IN0 + 4, ss), cnt * 56);
+      uint8_t* d_z = (uint8_t*)scratch_get(dc, ed_slot(SL_H_IN0 + 5, ss), cnt * 56);
+      if (!d_h || !d_z) return CAPY_ERR_OOM;
+      rc = dev_sign(ctx, dc, st, d_bits, sp.d_base, sp.d_off, sm.d_base, sm.d_off, cnt, d_h, d_z);
+      if (rc) return rc;
+      CAPY_CUDA(ctx, cudaMemcpyAsync(h56 + 56 * ch.i0, d_h, cnt * 56, cudaMemcpyDeviceToHost, st));
+      CAPY_CUDA(ctx, cudaMemcpyAsync(z_be56 + 56 * ch.i0, d_z, cnt * 56, cudaMemcpyDeviceToHost, st));
+      return CAPY_OK;
+    });
   });
 }
 
@@ -474,26 +515,25 @@ int capy_ed448_verify_batch(capy_ctx* ctx, int d_bits, const uint8_t* pub_xy112,
   std::vector<int> flags(ctx->devs.size(), 0);
   auto shards = split_items(msg_off, 0, 0, n, ctx->devs.size(), 4096);
   int rc = for_each_device(ctx, shards, [&](DeviceCtx& dc, Range sh) -> int {
-    cudaStream_t st = dc.streams[0];
-    const uint64_t cnt = sh.i1 - sh.i0;
-    StagedPacked sm;
-    uint8_t *d_pub = nullptr, *d_h = nullptr, *d_z = nullptr;
-    int rc = stage_packed(ctx, dc, st, SL_H_IN0, SL_H_IN0 + 1, msgs, msg_off, sh.i0, sh.i1, &sm);
-    if (rc) return rc;
-    rc = h2d(ctx, dc, st, SL_H_IN0 + 2, pub_xy112 + 112 * sh.i0, cnt * 112, &d_pub);
-    if (rc) return rc;
-    rc = h2d(ctx, dc, st, SL_H_IN0 + 3, h56 + 56 * sh.i0, cnt * 56, &d_h);
-    if (rc) return rc;
-    rc = h2d(ctx, dc, st, SL_H_IN0 + 4, z_be56 + 56 * sh.i0, cnt * 56, &d_z);
-    if (rc) return rc;
-    uint8_t* d_ok = (uint8_t*)scratch_get(dc, SL_H_IN0 + 5, cnt);
-    int* d_flag = (int*)scratch_get(dc, SL_FLAG, sizeof(int));
-    if (!d_ok || !d_flag) return CAPY_ERR_OOM;
-    CAPY_CUDA(ctx, cudaMemsetAsync(d_flag, 0, sizeof(int), st));
-    rc = dev_verify(ctx, dc, st, d_bits, d_pub, sm.d_base, sm.d_off, d_h, d_z, cnt, d_ok, d_flag);
-    if (rc) return rc;
-    CAPY_CUDA(ctx, cudaMemcpyAsync(ok + sh.i0, d_ok, cnt, cudaMemcpyDeviceToHost, st));
-    return read_flag(ctx, st, d_flag, &flags[dc.index]);
+    return ed_host_chunks(ctx, dc, sh, &flags[dc.index], [&](cudaStream_t st, int ss, Range ch, int* d_flag) -> int {
+      const uint64_t cnt = ch.i1 - ch.i0;
+      StagedPacked sm;
+      uint8_t *d_pub = nullptr, *d_h = nullptr, *d_z = nullptr;
+      int rc = stage_packed(ctx, dc, st, ed_slot(SL_H_IN0, ss), ed_slot(SL_H_IN0 + 1, ss), msgs, msg_off, ch.i0, ch.i1, &sm);
+      if (rc) return rc;
+      rc = h2d(ctx, dc, st, ed_slot(SL_H_IN0 + 2, ss), pub_xy112 + 112 * ch.i0, cnt * 112, &d_pub);
+      if (rc) return rc;
+      rc = h2d(ctx, dc, st, ed_slot(SL_H_IN0 + 3, ss), h56 + 56 * ch.i0, cnt * 56, &d_h);
+      if (rc) return rc;
+      rc = h2d(ctx, dc, st, ed_slot(SL_H_IN0 + 4, ss), z_be56 + 56 * ch.i0, cnt * 56, &d_z);
+      if (rc) return rc;
+      uint8_t* d_ok = (uint8_t*)scratch_get(dc, ed_slot(SL_H_IN0 + 5, ss), cnt);
+      if (!d_ok) return CAPY_ERR_OOM;
+      rc = dev_verify(ctx, dc, st, d_bits, d_pub, sm.d_base, sm.d_off, d_h, d_z, cnt, d_ok, d_flag);
+      if (rc) return rc;
+      CAPY_CUDA(ctx, cudaMemcpyAsync(ok + ch.i0, d_ok, cnt, cudaMemcpyDeviceToHost, st));
+      return CAPY_OK;
+    });
   });
   if (rc) return rc;
   for (int f : flags)
@@ -508,41 +548,40 @@ int capy_ed448_ecdh_batch(capy_ctx* ctx, const uint8_t* k_rand56, const uint8_t*
   std::vector<int> flags(ctx->devs.size(), 0);
   auto shards = split_items(nullptr, 1, 0, n, ctx->devs.size(), 0);
   int rc = for_each_device(ctx, shards, [&](DeviceCtx& dc, Range sh) -> int {
-    cudaStream_t st = dc.streams[0];
-    const uint64_t cnt = sh.i1 - sh.i0;
-    uint8_t *d_k = nullptr, *d_pub = nullptr;
-    int rc = h2d(ctx, dc, st, SL_H_IN0, k_rand56 + 56 * sh.i0, cnt * 56, &d_k);
-    if (rc) return rc;
-    rc = h2d(ctx, dc, st, SL_H_IN0 + 1, pub_xy112 + 112 * sh.i0, cnt * 112, &d_pub);
-    if (rc) return rc;
-    uint8_t* d_wx = (uint8_t*)scratch_get(dc, SL_H_IN0 + 2, cnt * 56);
-    uint32_t* proj = (uint32_t*)scratch_get(dc, SL_PROJ, cnt * 256);
-    uint8_t* bad = (uint8_t*)scratch_get(dc, SL_BAD, cnt);
-    int* d_flag = (int*)scratch_get(dc, SL_FLAG, sizeof(int));
-    if (!d_wx || !proj || !bad || !d_flag) return CAPY_ERR_OOM;
-    CAPY_CUDA(ctx, cudaMemsetAsync(d_flag, 0, sizeof(int), st));
-    // W = [k]V with k = 4 * BE(rand) mod r (ecc/encryptable.rs:36-37); W.x
-    rc = launch_var_base(ctx, dc, st, d_k, 1, d_pub, nullptr, proj, bad, cnt, true);
-    if (rc) return rc;
-    rc = launch_to_affine(ctx, st, proj, cnt, 1, bad, d_wx);
-    if (rc) return rc;
-    any_bad_kernel<<<grid_for(cnt, 256), 256, 0, st>>>(bad, d_flag, cnt);
-    ctx->launches++;
-    CAPY_CUDA(ctx, cudaGetLastError());
-    CAPY_CUDA(ctx, cudaMemcpyAsync(wx56 + 56 * sh.i0, d_wx, cnt * 56, cudaMemcpyDeviceToHost, st));
-    if (z_xy112) {  // Z = [k]G (:38)
-      uint32_t* kw = (uint32_t*)scratch_get(dc, SL_KWORDS, cnt * 56);
-      uint8_t* d_z = (uint8_t*)scratch_get(dc, SL_H_IN0 + 3, cnt * 112);
-      if (!kw || !d_z) return CAPY_ERR_OOM;
-      rc = launch_scalar_prep(ctx, st, d_k, 1, kw, nullptr, cnt);
+    return ed_host_chunks(ctx, dc, sh, &flags[dc.index], [&](cudaStream_t st, int ss, Range ch, int* d_flag) -> int {
+      const uint64_t cnt = ch.i1 - ch.i0;
+      uint8_t *d_k = nullptr, *d_pub = nullptr;
+      int rc = h2d(ctx, dc, st, ed_slot(SL_H_IN0, ss), k_rand56 + 56 * ch.i0, cnt * 56, &d_k);
       if (rc) return rc;
-      rc = launch_fixed_base(ctx, dc, st, kw, proj, cnt, true);
+      rc = h2d(ctx, dc, st, ed_slot(SL_H_IN0 + 1, ss), pub_xy112 + 112 * ch.i0, cnt * 112, &d_pub);
       if (rc) return rc;
-      rc = launch_to_affine(ctx, st, proj, cnt, 0, nullptr, d_z);
+      uint8_t* d_wx = (uint8_t*)scratch_get(dc, ed_slot(SL_H_IN0 + 2, ss), cnt * 56);
+      uint32_t* proj = (uint32_t*)scratch_get(dc, ed_slot(SL_PROJ, ss), cnt * 256);
+      uint8_t* bad = (uint8_t*)scratch_get(dc, ed_slot(SL_BAD, ss), cnt);
+      if (!d_wx || !proj || !bad) return CAPY_ERR_OOM;
+      // W = [k]V with k = 4 * BE(rand) mod r (ecc/encryptable.rs:36-37); W.x
+      rc = launch_var_base(ctx, dc, st, d_k, 1, d_pub, nullptr, proj, bad, cnt, true);
       if (rc) return rc;
-      CAPY_CUDA(ctx, cudaMemcpyAsync(z_xy112 + 112 * sh.i0, d_z, cnt * 112, cudaMemcpyDeviceToHost, st));
-    }
-    return read_flag(ctx, st, d_flag, &flags[dc.index]);
+      rc = launch_to_affine(ctx, st, proj, cnt, 1, bad, d_wx);
+      if (rc) return rc;
+      any_bad_kernel<<<grid_for(cnt, 256), 256, 0, st>>>(bad, d_flag, cnt);
+      ctx->launches++;
+      CAPY_CUDA(ctx, cudaGetLastError());
+      CAPY_CUDA(ctx, cudaMemcpyAsync(wx56 + 56 * ch.i0, d_wx, cnt * 56, cudaMemcpyDeviceToHost, st));
+      if (z_xy112) {  // Z = [k]G (:38)
+        uint32_t* kw = (uint32_t*)scratch_get(dc, ed_slot(SL_KWORDS, ss), cnt * 56);
+        uint8_t* d_z = (uint8_t*)scratch_get(dc, ed_slot(SL_H_IN0 + 3, ss), cnt * 112);
+        if (!kw || !d_z) return CAPY_ERR_OOM;
+        rc = launch_scalar_prep(ctx, st, d_k, 1, kw, nullptr, cnt);
+        if (rc) return rc;
+        rc = launch_fixed_base(ctx, dc, st, kw, proj, cnt, true);
+        if (rc) return rc;
+        rc = launch_to_affine(ctx, st, proj, cnt, 0, nullptr, d_z);
+        if (rc) return rc;
+        CAPY_CUDA(ctx, cudaMemcpyAsync(z_xy112 + 112 * ch.i0, d_z, cnt * 112, cudaMemcpyDeviceToHost, st));
+      }
+      return CAPY_OK;
+    });
   });
   if (rc) return rc;
   for (int f : flags)

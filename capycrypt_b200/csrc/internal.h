@@ -19,7 +19,7 @@
 namespace capy {
 
 constexpr int kNumStreams = 3;
-constexpr int kNumScratch = 80;  // 0..23 sponge entry points, 24..55 Ed448 pipelines, 56..79 AE pipelines
+constexpr int kNumScratch = 144;  // 0..23 sponge entry points, 24..55 Ed448 pipelines, 56..79 AE pipelines, 80..143 Ed448 slots of streams 1, 2
 
 // grow-only device scratch slots; each API call uses a fixed set of slot ids
 struct Scratch {
