@@ -45,6 +45,7 @@ SIGNATURES = {
     "capy_plan_tiers3": (i32, [vp, u32, u64, u32, u64, i32, vp, vp]),
     "capy_gpu_set_plan_cache": (i32, [vp, i32]),
     "capy_lpt_shares": (i32, [vp, u64, u32, u32, u64, vp]),
+    "capy_chain_cut": (i32, [i32, u64, u64, u64, vp]),
     "capy_sha3_batch": (i32, [vp, i32, u8p, u64p, u64, u8p, u32]),
     "capy_sha3_batch_fixed": (i32, [vp, i32, u8p, u64, u64, u64, u8p, u32]),
     "capy_sha3_batch_dev": (i32, [vp, i32, vp, i32, u8p, u64p, u64, u8p, u32]),

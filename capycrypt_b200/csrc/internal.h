@@ -19,7 +19,8 @@
 namespace capy {
 
 constexpr int kNumStreams = 3;
-constexpr int kNumScratch = 144;  // 0..23 sponge entry points, 24..55 Ed448 pipelines, 56..79 AE pipelines, 80..143 Ed448 slots of streams 1, 2
+constexpr int kNumScratch = 152;  // 0..23 sponge entry points, 24..55 Ed448 pipelines, 56..79 AE pipelines, 80..143 Ed448 slots of streams 1, 2,
+                                  // 144..151 chain hand-off (states, tickets) of the sponge entry points
 
 // grow-only device scratch slots; each API call uses a fixed set of slot ids
 struct Scratch {
@@ -42,6 +43,7 @@ struct LaunchPlan {
   int warps_per_smsp = 0;   // 0 = unthrottled
   uint64_t warp_items[3] = {0, 0, 0};  // one warp per item: [c - 1] of them run c chains per scheduler (ranks in this order)
   uint64_t pair_items = 0;             // the next ranks: two threads per item
+  uint64_t uniform_blocks = 0;         // != 0: every item holds this many whole blocks (+ a partial one): nothing to order
 };
 
 // Cached plan of a ragged batch, keyed by the caller's offsets array (capy_gpu_set_plan_cache): a repeated call with the

@@ -5,6 +5,8 @@
 // The SP 800-185 encoders (aux_functions.rs:11-68) run on the host only to build the constant
 // prefix block of cSHAKE/KMAC; every byte that is absorbed per item is produced on the device.
 #include <algorithm>
+#include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <thread>
 #include <vector>
@@ -352,7 +354,10 @@ static int plan_ragged(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t st, const uint
     const uint64_t len0 = h_off[1] - h_off[0];
     bool uniform = true;
     for (uint64_t i = 1; i < n && uniform; i++) uniform = (h_off[i + 1] - h_off[i]) == len0;
-    if (uniform) return CAPY_OK;  // nothing to order, no chain stands out
+    if (uniform) {  // nothing to order, no chain stands out
+      plan->uniform_blocks = len0 / stride_bytes + 1;
+      return CAPY_OK;
+    }
     if (n > kHostPlanMaxItems) {
       h_off = nullptr;  // a histogram of millions of items is cheaper on the device, round trip included
     } else {
@@ -437,6 +442,7 @@ static int plan_ragged(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t st, const uint
     }
     plan_tiers(cum, n, max_blocks, (double)total_blocks, dc.sm_count, plan->warp_items, &plan->pair_items, force_c);
   }
+  if (bins == 1) plan->uniform_blocks = max_blocks;
   if (bins > 1) {  // (uniform lengths: nothing to order)
     len_scatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_off, n, stride_bytes, hist, order);
     ctx->launches++;
@@ -741,6 +747,74 @@ static void fill_cshake_common(SpongeJob& J, int d, const PrefixState* ps) {
   J.sq_lanes = (1600 - d) / 64;
 }
 
+// ---- chain splitting of uniform batches (sponge.cuh: sponge_chain_kernel) --------------------------------------------
+// Where to cut: the batch must fill the schedulers unevenly, be large enough that no job-1 block has to wait for its
+// job-0 block (at least as many job-0 blocks as the GPU holds at once: CAPY_SPONGE_MINB per SM), and leave the two halves
+// about equally long; the cut lies inside -- or at the end of -- the absorb phase.  absorb_blocks counts the blocks after
+// skip_blocks, squeeze_extra the permutations between squeeze blocks.  (A wrong estimate costs balance, never
+// correctness: an item that is shorter than the cut simply has nothing left to absorb in job 1.)
+static bool chain_cut(int sm_count, uint64_t n, uint64_t absorb_blocks, uint64_t squeeze_extra, uint64_t* cut) {
+  if (getenv("CAPY_NO_CHAIN_SPLIT")) return false;  // A/B switch for the probes
+  if (sm_count < 1) return false;
+  const uint64_t warps = (n + 31) / 32, sched = 4ull * (uint64_t)sm_count, blocks = (n + 127) / 128;
+  if (blocks < (uint64_t)CAPY_SPONGE_MINB * (uint64_t)sm_count || warps > 8 * sched) return false;
+  auto fill = [&](uint64_t w) {
+    const double x = (double)w / (double)sched;
+    return x / std::ceil(x);
+  };
+  if (fill(2 * warps) < fill(warps) + 0.04) return false;
+  const uint64_t perms = absorb_blocks + squeeze_extra;
+  if (perms < 12) return false;
+  uint64_t k = (perms + 1) / 2;
+  if (k > absorb_blocks) k = absorb_blocks;
+  if (3 * k < perms) return false;  // the absorb phase is too short to carry a half
+  *cut = k;
+  return true;
+}
+
+template <int LANES>
+static int launch_chain_t(capy_ctx* ctx, cudaStream_t stream, const SpongeChain& C, unsigned grid) {
+  sponge_chain_kernel<LANES><<<grid, 128, 0, stream>>>(C);
+  ctx->launches++;
+  CAPY_CUDA(ctx, cudaGetLastError());
+  return CAPY_OK;
+}
+
+// J (uniform batch, no order) as two dependent jobs cut after `cut` absorbed blocks
+static int launch_sponge_chain(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t stream, int lanes, const SpongeJob& J, uint64_t cut) {
+  int si = 0;
+  for (int k = 0; k < kNumStreams; k++)
+    if (dc.streams[k] == stream) si = k;
+  const uint32_t nb = (uint32_t)((J.n + 127) / 128);
+  uint64_t* states = (uint64_t*)scratch_get(dc, 144 + 2 * si, (size_t)J.n * 25 * sizeof(uint64_t));
+  uint32_t* sync = (uint32_t*)scratch_get(dc, 145 + 2 * si, ((size_t)nb + 1) * sizeof(uint32_t));
+  if (!states || !sync) return CAPY_ERR_OOM;
+  CAPY_CUDA(ctx, cudaMemsetAsync(sync, 0, ((size_t)nb + 1) * sizeof(uint32_t), stream));
+  SpongeChain C;
+  C.j[0] = J;
+  C.j[0].chain_out = states;
+  C.j[0].stop_block = J.skip_blocks + cut;
+  C.j[1] = J;
+  C.j[1].chain_in = states;
+  C.j[1].skip_blocks = (uint32_t)(J.skip_blocks + cut);
+  C.sync = sync;
+  C.blocks_per_job = nb;
+  switch (lanes) {
+    case 17: return launch_chain_t<17>(ctx, stream, C, 2 * nb);
+    case 19: return launch_chain_t<19>(ctx, stream, C, 2 * nb);
+    case 21: return launch_chain_t<21>(ctx, stream, C, 2 * nb);
+    default: return CAPY_ERR_BAD_ARG;
+  }
+}
+
+// blocks a uniform cSHAKE / KMAC item absorbs after the cached prefix, estimated from the message blocks of the plan
+static uint64_t absorb_blocks_estimate(const SpongeJob& J, uint64_t key_len, bool has_key, uint64_t msg_blocks_whole) {
+  uint64_t blocks = msg_blocks_whole + 1;  // the message and the block that holds its tail, the trailer and the pad
+  if (has_key) blocks += (key_len + 8) / J.w + 1;  // bytepad(encode_string(K), w)
+  if (!J.skip_blocks) blocks += J.prefix_len / J.rate;
+  return blocks;
+}
+
 static int launch_cshake(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t stream, int d, const uint8_t* data,
                          const uint64_t* off, uint64_t n, const uint8_t* fn, uint32_t fn_len, const uint8_t* cs,
                          uint32_t cs_len, uint64_t out_bits, uint8_t* out) {
@@ -765,7 +839,14 @@ static int launch_cshake(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t stream, int 
     if (rc) return rc;
   }
   J.order = plan.order;
-  return launch_sponge(ctx, dc, stream, (int)(bytepad_value(d) * 8 / 64), J, plan);
+  const int lanes = (int)(bytepad_value(d) * 8 / 64);
+  if (off && !plan.order && plan.uniform_blocks && (J.rate & 7u) == 0) {  // uniform batch: see launch_kmac_xof
+    const uint64_t absorb = absorb_blocks_estimate(J, 0, false, plan.uniform_blocks - 1);
+    const uint64_t sq = 8ull * J.sq_lanes, squeeze_extra = (J.out_bytes + sq - 1) / sq - 1;
+    uint64_t cut;
+    if (chain_cut(dc.sm_count, n, absorb, squeeze_extra, &cut)) return launch_sponge_chain(ctx, dc, stream, lanes, J, cut);
+  }
+  return launch_sponge(ctx, dc, stream, lanes, J, plan);
 }
 
 static int build_kmac_job(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t stream, const KmacDevArgs& a, SpongeJob* out) {
@@ -815,7 +896,17 @@ int launch_kmac_xof(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t stream, const Kma
   rc = plan_kmac(ctx, dc, stream, a, J, &plan);
   if (rc) return rc;
   J.order = plan.order;
-  return launch_sponge(ctx, dc, stream, (int)(bytepad_value(a.d_bits) * 8 / 64), J, plan);
+  const int lanes = (int)(bytepad_value(a.d_bits) * 8 / 64);
+  // uniform batch (fixed-length call, or a plan that found one block count): cut the chains when that fills the GPU better
+  const uint64_t unit = J.rate & ~7u;
+  const uint64_t msg_blocks = a.off ? plan.uniform_blocks : a.msg_len / unit + 1;
+  if (!a.out_off && !a.xor_in && !plan.order && msg_blocks && (J.rate & 7u) == 0) {
+    const uint64_t absorb = absorb_blocks_estimate(J, a.key_len, a.keys != nullptr, msg_blocks - 1);
+    const uint64_t sq = 8ull * J.sq_lanes, squeeze_extra = a.out_bytes ? (a.out_bytes + sq - 1) / sq - 1 : 0;
+    uint64_t cut;
+    if (chain_cut(dc.sm_count, a.n, absorb, squeeze_extra, &cut)) return launch_sponge_chain(ctx, dc, stream, lanes, J, cut);
+  }
+  return launch_sponge(ctx, dc, stream, lanes, J, plan);
 }
 
 // Two independent KMACXOF passes over the same items (same d, same n) as ONE launch: warps alternate between the two
@@ -892,6 +983,12 @@ int capy_plan_tiers3(const uint32_t* items_longer_than, uint32_t n_bins, uint64_
   std::vector<uint32_t> cum(items_longer_than, items_longer_than + n_bins);
   plan_tiers(cum, n, max_blocks, (double)total_blocks, sm_count, warp_items_by_sharing, pair_items);
   return CAPY_OK;
+}
+
+int capy_chain_cut(int sm_count, uint64_t n, uint64_t absorb_blocks, uint64_t squeeze_extra, uint64_t* cut_after_blocks) {
+  if (!cut_after_blocks) return CAPY_ERR_BAD_ARG;
+  *cut_after_blocks = 0;
+  return chain_cut(sm_count, n, absorb_blocks, squeeze_extra, cut_after_blocks) ? 1 : 0;
 }
 
 int capy_lpt_shares(const uint64_t* off, uint64_t n, uint32_t parts, uint32_t unit_bytes, uint64_t per_item_cost,

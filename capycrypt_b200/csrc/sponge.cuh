@@ -69,6 +69,12 @@ struct SpongeJob {
   // [warp_items, first) two threads per item, [first, n) one thread per item
   uint64_t warp_items;
   uint64_t first;
+  // chain hand-off (sponge_chain_kernel): the chains of a uniform batch are cut in two segments that run as dependent jobs.
+  //   chain_out != nullptr: absorb blocks [skip_blocks, stop_block) only, then store the 25 lanes at chain_out[k * n + rank]
+  //   chain_in  != nullptr: start from the lanes another segment stored there (instead of init_state), at block skip_blocks
+  uint64_t* chain_out;
+  const uint64_t* chain_in;
+  uint64_t stop_block;
 };
 
 __device__ __forceinline__ uint32_t left_encode_nbytes(uint64_t v) {
@@ -198,12 +204,21 @@ struct SpongeGeom {
 // =====================================================================================================
 // one thread per item
 // =====================================================================================================
-template <int LANES>
-__device__ __forceinline__ void sponge_item(const SpongeJob& J, uint64_t i) {
+// CHAIN: the item may start from / stop at a handed-over state (rank = its slot in the hand-off arrays); the plain
+// kernels instantiate CHAIN = false and compile to what they were.
+template <int LANES, bool CHAIN = false>
+__device__ __forceinline__ void sponge_item(const SpongeJob& J, uint64_t i, uint64_t rank = 0) {
   SpongeGeom g;
   g.init(J, i);
   Lane a[25];
-  if (J.init_state) {
+  if (CHAIN && J.chain_in) {
+#pragma unroll
+    for (int k = 0; k < 25; k++) {
+      const uint64_t v = __ldcg(J.chain_in + (uint64_t)k * J.n + rank);  // written by another SM in this launch: L2, not L1
+      a[k].lo = (uint32_t)v;
+      a[k].hi = (uint32_t)(v >> 32);
+    }
+  } else if (J.init_state) {
 #pragma unroll
     for (int k = 0; k < 25; k++) {
       const uint64_t v = J.init_state[k];
@@ -222,7 +237,12 @@ __device__ __forceinline__ void sponge_item(const SpongeJob& J, uint64_t i) {
   constexpr uint64_t STRIDE = 8ull * LANES;  // bytes consumed per block (168 for the 172 quirk)
   uint64_t fb0, fb1;
   g.fast_range(STRIDE, J.skip_blocks, fb0, fb1);
-  const uint64_t nblocks = g.nblocks;
+  uint64_t nblocks = g.nblocks;
+  if (CHAIN && J.chain_out) {  // this segment ends at stop_block
+    nblocks = nblocks < J.stop_block ? nblocks : J.stop_block;
+    fb0 = fb0 < nblocks ? fb0 : nblocks;
+    fb1 = fb1 < nblocks ? fb1 : nblocks;
+  }
 
   auto slow_block = [&](uint64_t b) {
     const uint64_t s = b * STRIDE;
@@ -308,6 +328,12 @@ __device__ __forceinline__ void sponge_item(const SpongeJob& J, uint64_t i) {
 
 #pragma unroll 1
   for (uint64_t b = fb1; b < nblocks; b++) slow_block(b);
+
+  if (CHAIN && J.chain_out) {  // hand the state to the next segment (coalesced: lane k of rank r at [k * n + r])
+#pragma unroll
+    for (int k = 0; k < 25; k++) J.chain_out[(uint64_t)k * J.n + rank] = ((uint64_t)a[k].hi << 32) | a[k].lo;
+    return;
+  }
 
   // ---- squeeze (sponge.rs:25-34, minus the dropped final permutation) -----------------------
   uint8_t* o;
@@ -610,6 +636,40 @@ __global__ void __launch_bounds__(128, CAPY_SPONGE_MINB) sponge_kernel2(const __
   const uint64_t r = ((t >> 6) << 5) | (t & 31u);
   if (r >= J.n) return;
   sponge_item<LANES>(J, sponge_rank_item(J, r));
+}
+
+// A uniform batch whose warps fill the schedulers unevenly (2^16 items = 3.46 warps per scheduler: a quarter of the
+// schedulers carry a fourth warp and everybody waits for them) is cut in two along the chains: job 0 absorbs the first
+// half of every item's blocks and stores the state, job 1 picks the states up and finishes.  Twice the warps, half as long
+// each: 6.92 per scheduler.  Both jobs are ONE launch; a block takes a ticket when it starts, the first `blocks_per_job`
+// tickets work on job 0, the others on job 1, and a job-1 block waits for the job-0 block of the same items (which holds a
+// smaller ticket, so it is running or done: no deadlock).  The launcher only cuts batches with at least as many job-0
+// blocks as the GPU holds at once, so in practice nobody waits.
+struct SpongeChain {
+  SpongeJob j[2];
+  uint32_t* sync;  // [0] ticket counter, [1 + b] warps of job-0 block b that have stored their states; zeroed before the launch
+  uint32_t blocks_per_job;
+};
+template <int LANES>
+__global__ void __launch_bounds__(128, CAPY_SPONGE_MINB) sponge_chain_kernel(const __grid_constant__ SpongeChain C) {
+  __shared__ uint32_t ticket_s;
+  if (threadIdx.x == 0) ticket_s = atomicAdd(C.sync, 1u);
+  __syncthreads();
+  const uint32_t ticket = ticket_s, nb = C.blocks_per_job;
+  const uint32_t job = ticket >= nb ? 1u : 0u, b = job ? ticket - nb : ticket;
+  const SpongeJob& J = C.j[job];
+  uint32_t* done = C.sync + 1 + b;
+  if (job) {
+    while (*reinterpret_cast<volatile uint32_t*>(done) < 4u) __nanosleep(64);
+    __threadfence();
+  }
+  const uint64_t r = (uint64_t)b * 128 + threadIdx.x;
+  if (r < J.n) sponge_item<LANES, true>(J, sponge_rank_item(J, r), r);
+  if (!job) {
+    __threadfence();  // this thread's state is visible before the warp reports
+    __syncwarp();
+    if ((threadIdx.x & 31u) == 0) atomicAdd(done, 1u);
+  }
 }
 
 // Chain-bound ragged batch in ONE launch, three tiers by rank in the length-sorted order:

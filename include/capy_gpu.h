@@ -109,6 +109,14 @@ int capy_plan_tiers(const uint32_t* items_longer_than, uint32_t n_bins, uint64_t
 int capy_plan_tiers3(const uint32_t* items_longer_than, uint32_t n_bins, uint64_t n, uint32_t max_blocks,
                      uint64_t total_blocks, int sm_count, uint64_t* warp_items_by_sharing, uint64_t* pair_items);
 
+/* ---- diagnostics: chain cutting of uniform cSHAKE / KMAC batches (no GPU needed) ------------------------------------
+ * A uniform batch whose warps fill the schedulers unevenly (2^16 items on 148 SMs = 3.46 warps per scheduler) is run
+ * as two dependent jobs in one launch: the first absorbs `cut_after_blocks` blocks of every item and hands the state
+ * over, the second finishes (twice the warps, half as long each).  Returns 1 and the cut when the engine would do that
+ * for n items that absorb absorb_blocks blocks (after the cached prefix) and run squeeze_extra permutations between
+ * squeeze blocks, 0 when the batch is launched as it is. */
+int capy_chain_cut(int sm_count, uint64_t n, uint64_t absorb_blocks, uint64_t squeeze_extra, uint64_t* cut_after_blocks);
+
 /* ---- diagnostics: how a ragged sponge batch is divided over the devices of a ctx (no GPU needed) ------------------- */
 /* owner[i] = index of the device that hashes item i when capy_sha3_batch runs on a ctx of `parts` devices: the outliers
  * (messages that cost >= 8 x the average, cost = len / unit_bytes + per_item_cost permutations) are dealt out longest

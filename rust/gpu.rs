@@ -36,6 +36,8 @@ extern "C" {
         sm_count: c_int, warp_items: *mut u64, pair_items: *mut u64) -> c_int;
     fn capy_plan_tiers3(items_longer_than: *const u32, n_bins: u32, n: u64, max_blocks: u32, total_blocks: u64,
         sm_count: c_int, warp_items_by_sharing: *mut u64, pair_items: *mut u64) -> c_int;
+    fn capy_chain_cut(sm_count: c_int, n: u64, absorb_blocks: u64, squeeze_extra: u64,
+        cut_after_blocks: *mut u64) -> c_int;
     fn capy_lpt_shares(off: *const u64, n: u64, parts: u32, unit_bytes: u32, per_item_cost: u64,
         owner: *mut u32) -> c_int;
     fn capy_sha3_batch(ctx: *mut CapyCtx, d_bits: c_int, data: *const u8, off: *const u64, n: u64, digests: *mut u8,

@@ -1,0 +1,118 @@
+"""GPU: uniform cSHAKE / KMAC batches that the engine cuts into two dependent jobs (sponge_chain_kernel: the first job
+absorbs half of every item's blocks and hands the state over, the second finishes) must give the bytes of the uncut
+launch and of the oracle.  2^16 items on a 148-SM GPU is the shape that gets cut (BASELINE config 2).
+
+Matches kmac_xof / cshake (sha3/shake_functions.rs:49-89) over equal-length messages."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+N = 1 << 16
+
+
+def _would_cut(engine, absorb, squeeze_extra=0):
+    import torch
+
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    cut = C.c_uint64(0)
+    return engine.lib.capy_chain_cut(sms, N, absorb, squeeze_extra, C.byref(cut)) == 1
+
+
+def _both(fn):
+    """fn() with the cut enabled and disabled (CAPY_NO_CHAIN_SPLIT is read at every launch)"""
+    os.environ.pop("CAPY_NO_CHAIN_SPLIT", None)
+    a = fn()
+    os.environ["CAPY_NO_CHAIN_SPLIT"] = "1"
+    try:
+        b = fn()
+    finally:
+        os.environ.pop("CAPY_NO_CHAIN_SPLIT", None)
+    return a, b
+
+
+@pytest.mark.parametrize("d,mlen", [(512, 2040), (512, 2041), (512, 2176), (512, 2177), (256, 2520), (256, 2600), (384, 2500)])
+def test_kmac_fixed_cut_equals_uncut_and_oracle(engine, oracle, d, mlen):
+    rate = (1600 - d) // 8
+    assert _would_cut(engine, 1 + mlen // rate + 1), "the shape under test is supposed to be cut on this GPU"
+    g = torch.Generator(device="cuda")
+    g.manual_seed(d + mlen)
+    data = torch.randint(0, 256, (N * mlen,), dtype=torch.uint8, device="cuda", generator=g)
+    keys = torch.randint(0, 256, (N * 32,), dtype=torch.uint8, device="cuda", generator=g)
+
+    def run():
+        out = torch.zeros(N * 64, dtype=torch.uint8, device="cuda")
+        engine.kmac_xof_fixed_dev(keys, 32, 32, data, mlen, mlen, N, 512, b"My Tagged Application", d, out)
+        torch.cuda.synchronize()
+        return out
+
+    cut, plain = _both(run)
+    assert torch.equal(cut, plain)
+    pick = np.sort(np.random.default_rng(mlen).choice(N, size=48, replace=False))
+    idx = torch.from_numpy(pick).cuda()
+    s_data = data.view(N, mlen)[idx].cpu().numpy().reshape(-1)
+    s_keys = keys.view(N, 32)[idx].cpu().numpy().reshape(-1)
+    want = oracle.kmac_xof_batch(s_keys, np.arange(49, dtype=np.uint64) * 32, s_data, np.arange(49, dtype=np.uint64) * mlen, 512,
+                                 b"My Tagged Application", d)
+    assert np.array_equal(cut.view(N, 64)[idx].cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("out_bytes", [64, 2000])
+def test_cshake_and_kmac_with_offsets_and_long_outputs(engine, oracle, out_bytes):
+    """offsets arrays on the device (the plan finds one block count), 2 000-byte outputs: the cut lies at the end of the absorb"""
+    mlen = 2100
+    g = torch.Generator(device="cuda")
+    g.manual_seed(out_bytes)
+    data = torch.randint(0, 256, (N * mlen,), dtype=torch.uint8, device="cuda", generator=g)
+    keys = torch.randint(0, 256, (N * 40,), dtype=torch.uint8, device="cuda", generator=g)
+    off = torch.arange(N + 1, dtype=torch.int64, device="cuda") * mlen
+    koff = torch.arange(N + 1, dtype=torch.int64, device="cuda") * 40
+
+    def cshake():
+        out = torch.zeros(N * out_bytes, dtype=torch.uint8, device="cuda")
+        engine.cshake_dev(data, off, 8 * out_bytes, b"", b"Email Signature", 512, out)
+        torch.cuda.synchronize()
+        return out
+
+    def kmac():
+        out = torch.zeros(N * out_bytes, dtype=torch.uint8, device="cuda")
+        engine.kmac_xof_dev(keys, koff, data, off, 8 * out_bytes, b"tag", 512, out)
+        torch.cuda.synchronize()
+        return out
+
+    pick = np.sort(np.random.default_rng(out_bytes).choice(N, size=24, replace=False))
+    idx = torch.from_numpy(pick).cuda()
+    s_data = data.view(N, mlen)[idx].cpu().numpy().reshape(-1)
+    s_off = np.arange(25, dtype=np.uint64) * mlen
+    c_cut, c_plain = _both(cshake)
+    assert torch.equal(c_cut, c_plain)
+    assert np.array_equal(c_cut.view(N, out_bytes)[idx].cpu().numpy(),
+                          oracle.cshake_batch(s_data, s_off, 8 * out_bytes, b"", b"Email Signature", 512))
+    k_cut, k_plain = _both(kmac)
+    assert torch.equal(k_cut, k_plain)
+    s_keys = keys.view(N, 40)[idx].cpu().numpy().reshape(-1)
+    assert np.array_equal(k_cut.view(N, out_bytes)[idx].cpu().numpy(),
+                          oracle.kmac_xof_batch(s_keys, np.arange(25, dtype=np.uint64) * 40, s_data, s_off, 8 * out_bytes, b"tag", 512))
+
+
+def test_host_entry_point_with_ragged_keys(engine, oracle):
+    """capy_kmac_xof_batch: equal-length messages (found from the host offsets), keys of different lengths -- some items
+    have one key block, some two, so the cut is not at the same place of every stream; still the same bytes"""
+    mlen, n = 1800, N
+    rnd = np.random.default_rng(9)
+    data = rnd.integers(0, 256, size=n * mlen, dtype=np.uint8)
+    off = np.arange(n + 1, dtype=np.uint64) * mlen
+    klens = rnd.choice([0, 16, 32, 131, 140, 267], size=n)
+    koff = np.concatenate([[0], np.cumsum(klens)]).astype(np.uint64)
+    keys = rnd.integers(0, 256, size=int(koff[-1]), dtype=np.uint8)
+    cut, plain = _both(lambda: engine.kmac_xof(keys, koff, data, off, 512, b"", 512))
+    assert np.array_equal(cut, plain)
+    pick = np.sort(rnd.choice(n, size=64, replace=False))
+    s_keys = np.concatenate([keys[int(koff[i]):int(koff[i + 1])] for i in pick])
+    s_koff = np.concatenate([[0], np.cumsum(klens[pick])]).astype(np.uint64)
+    s_data = data.reshape(n, mlen)[pick].reshape(-1)
+    assert np.array_equal(cut[pick], oracle.kmac_xof_batch(s_keys, s_koff, s_data, np.arange(65, dtype=np.uint64) * mlen, 512, b"", 512))
