@@ -106,14 +106,13 @@ static int dev_ae_open(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t st, const AeCo
   k.out_off = off;
   k.out = out;
   k.xor_in = ct;
-  int rc = launch_kmac_xof(ctx, dc, st, k);
-  if (rc) return rc;
   KmacDevArgs a = ae_kmac_args(c, c.keymat + c.klen, n, c.ka_custom);
   a.data = out;
   a.off = off;
   a.out_bytes = a.out_stride = c.tag_bytes;
   a.out = t_new;
-  rc = launch_kmac_xof(ctx, dc, st, a);
+  // the tag pass reads what the keystream pass writes: dependent jobs of one launch when the batch is large enough
+  int rc = launch_kmac_xof_dep(ctx, dc, st, k, a);
   if (rc) return rc;
   ae_finish_kernel<<<grid_for(n * 32, 256), 256, 0, st>>>(t_new, tag, c.tag_bytes, bad, ct, off, out, ok, n);
   ctx->launches++;

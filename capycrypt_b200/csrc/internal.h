@@ -186,5 +186,7 @@ struct KmacDevArgs {
 int launch_kmac_xof(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t stream, const KmacDevArgs& a);
 // two passes over the same items (same d, same n) as one launch; the plan (work order) is taken from `a`
 int launch_kmac_xof2(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t stream, const KmacDevArgs& a, const KmacDevArgs& b);
+// two passes where `second` absorbs what `first` wrote for the same item: one launch of dependent jobs when the batch is large
+int launch_kmac_xof_dep(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t stream, const KmacDevArgs& first, const KmacDevArgs& second);
 
 }  // namespace capy

@@ -780,31 +780,43 @@ static int launch_chain_t(capy_ctx* ctx, cudaStream_t stream, const SpongeChain&
   return CAPY_OK;
 }
 
-// J (uniform batch, no order) as two dependent jobs cut after `cut` absorbed blocks
-static int launch_sponge_chain(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t stream, int lanes, const SpongeJob& J, uint64_t cut) {
-  int si = 0;
-  for (int k = 0; k < kNumStreams; k++)
-    if (dc.streams[k] == stream) si = k;
-  const uint32_t nb = (uint32_t)((J.n + 127) / 128);
-  uint64_t* states = (uint64_t*)scratch_get(dc, 144 + 2 * si, (size_t)J.n * 25 * sizeof(uint64_t));
-  uint32_t* sync = (uint32_t*)scratch_get(dc, 145 + 2 * si, ((size_t)nb + 1) * sizeof(uint32_t));
-  if (!states || !sync) return CAPY_ERR_OOM;
+static int chain_stream_index(const DeviceCtx& dc, cudaStream_t stream) {
+  for (int k = 1; k < kNumStreams; k++)
+    if (dc.streams[k] == stream) return k;
+  return 0;
+}
+
+// two jobs over the same ranks in one launch, job 1 of an item after job 0 of that item (sponge_chain_kernel)
+static int launch_chain_jobs(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t stream, int lanes, const SpongeJob& J0, const SpongeJob& J1,
+                             bool data_dependent) {
+  const uint32_t nb = (uint32_t)((J0.n + 127) / 128);
+  uint32_t* sync = (uint32_t*)scratch_get(dc, 145 + 2 * chain_stream_index(dc, stream), ((size_t)nb + 1) * sizeof(uint32_t));
+  if (!sync) return CAPY_ERR_OOM;
   CAPY_CUDA(ctx, cudaMemsetAsync(sync, 0, ((size_t)nb + 1) * sizeof(uint32_t), stream));
   SpongeChain C;
-  C.j[0] = J;
-  C.j[0].chain_out = states;
-  C.j[0].stop_block = J.skip_blocks + cut;
-  C.j[1] = J;
-  C.j[1].chain_in = states;
-  C.j[1].skip_blocks = (uint32_t)(J.skip_blocks + cut);
+  C.j[0] = J0;
+  C.j[1] = J1;
   C.sync = sync;
   C.blocks_per_job = nb;
+  C.data_dependent = data_dependent ? 1u : 0u;
   switch (lanes) {
     case 17: return launch_chain_t<17>(ctx, stream, C, 2 * nb);
     case 19: return launch_chain_t<19>(ctx, stream, C, 2 * nb);
     case 21: return launch_chain_t<21>(ctx, stream, C, 2 * nb);
     default: return CAPY_ERR_BAD_ARG;
   }
+}
+
+// J (uniform batch, no order) as two dependent jobs cut after `cut` absorbed blocks
+static int launch_sponge_chain(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t stream, int lanes, const SpongeJob& J, uint64_t cut) {
+  uint64_t* states = (uint64_t*)scratch_get(dc, 144 + 2 * chain_stream_index(dc, stream), (size_t)J.n * 25 * sizeof(uint64_t));
+  if (!states) return CAPY_ERR_OOM;
+  SpongeJob J0 = J, J1 = J;
+  J0.chain_out = states;
+  J0.stop_block = J.skip_blocks + cut;
+  J1.chain_in = states;
+  J1.skip_blocks = (uint32_t)(J.skip_blocks + cut);
+  return launch_chain_jobs(ctx, dc, stream, lanes, J0, J1, false);
 }
 
 // blocks a uniform cSHAKE / KMAC item absorbs after the cached prefix, estimated from the message blocks of the plan
@@ -958,6 +970,33 @@ int launch_kmac_xof2(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t stream, const Km
     case 21: return launch_sponge2_t<21>(ctx, stream, JA, JB, block, plan);
     default: return CAPY_ERR_BAD_ARG;
   }
+}
+
+// Two KMACXOF passes where the SECOND absorbs what the FIRST wrote for the same item (authenticated decryption: the
+// keystream pass recovers the plaintext, the tag pass runs over it -- sha3/encryptable.rs:66-75): one launch of
+// dependent jobs instead of two kernels, so the partial wave of the first pass is filled by the second.  Both follow the
+// plan (work order) of `second`.  Small or chain-bound batches run the two passes one after the other.
+int launch_kmac_xof_dep(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t stream, const KmacDevArgs& first, const KmacDevArgs& second) {
+  if (!valid_secparam(first.d_bits) || first.d_bits != second.d_bits || first.n != second.n) return CAPY_ERR_BAD_ARG;
+  if (first.n == 0) return CAPY_OK;
+  SpongeJob J0, J1;
+  int rc = build_kmac_job(ctx, dc, stream, first, &J0);
+  if (rc) return rc;
+  rc = build_kmac_job(ctx, dc, stream, second, &J1);
+  if (rc) return rc;
+  LaunchPlan plan;
+  rc = plan_kmac(ctx, dc, stream, second, J1, &plan);
+  if (rc) return rc;
+  J0.order = J1.order = plan.order;
+  const int lanes = (int)(bytepad_value(first.d_bits) * 8 / 64);
+  const bool tiers = plan.warp_items[0] || plan.warp_items[1] || plan.warp_items[2] || plan.pair_items;
+  const uint64_t blocks = (first.n + 127) / 128;
+  if (tiers || (J0.rate & 7u) != 0 || blocks < (uint64_t)CAPY_SPONGE_MINB * (uint64_t)dc.sm_count || getenv("CAPY_NO_CHAIN_SPLIT")) {
+    rc = launch_sponge(ctx, dc, stream, lanes, J0, plan);  // (a job-1 block of a small batch would wait for its job-0 block)
+    if (rc) return rc;
+    return launch_sponge(ctx, dc, stream, lanes, J1, plan);
+  }
+  return launch_chain_jobs(ctx, dc, stream, lanes, J0, J1, true);
 }
 
 }  // namespace capy

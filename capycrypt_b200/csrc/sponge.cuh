@@ -83,6 +83,25 @@ __device__ __forceinline__ uint32_t left_encode_nbytes(uint64_t v) {
   return nb;
 }
 
+// Loads of message bytes.  COH = true: the bytes were written earlier in the SAME launch by a block on another SM
+// (sponge_chain_kernel with a dependent job): they are read from the L2 (ld.global.cg), never from this SM's L1 --
+// a line the L1 fetched for the tail of one item may hold stale bytes of the next item's head.
+template <bool COH>
+__device__ __forceinline__ uint32_t ld_u8(const uint8_t* p) {
+  if constexpr (COH) return (uint32_t)__ldcg(p);
+  else return (uint32_t)*p;
+}
+template <bool COH>
+__device__ __forceinline__ uint2 ld_lane(const uint2* p) {
+  if constexpr (COH) return __ldcg(p);
+  else return __ldg(p);
+}
+template <bool COH>
+__device__ __forceinline__ uint32_t ld_word(const uint32_t* p) {
+  if constexpr (COH) return __ldcg(p);
+  else return __ldg(p);
+}
+
 // ---- per-item geometry of the virtual stream  P | KB | X | T | pad --------------------------------------
 struct SpongeGeom {
   const uint8_t* prefix;
@@ -158,11 +177,12 @@ struct SpongeGeom {
   }
 
   // bytes of the segment [seg0, seg1) (stream offsets; base[0] sits at seg0) that fall into the lane at o
+  template <bool COH = false>
   static __device__ __forceinline__ uint64_t piece(const uint8_t* base, uint64_t seg0, uint64_t seg1, uint64_t o) {
     const uint64_t lo = o > seg0 ? o : seg0, hi = o + 8 < seg1 ? o + 8 : seg1;
     uint64_t v = 0;
 #pragma unroll 1
-    for (uint64_t q = lo; q < hi; q++) v |= (uint64_t)base[q - seg0] << (8 * (uint32_t)(q - o));
+    for (uint64_t q = lo; q < hi; q++) v |= (uint64_t)ld_u8<COH>(base + (q - seg0)) << (8 * (uint32_t)(q - o));
     return v;
   }
 
@@ -170,19 +190,20 @@ struct SpongeGeom {
   // that overlap it, each piece fetched with a loop over just its own bytes; lanes wholly inside X, inside zero
   // padding or past the end take one compare each.  (The first version walked all 8 bytes of every lane through
   // a compare chain: ~2 700 instructions per block against ~700 now; KMAC over 4 KB has two such blocks in 33.)
+  template <bool COH = false>
   __device__ __forceinline__ uint64_t lane(uint64_t o) const {
     uint64_t v = 0;
     if (o >= x0 && o + 8 <= x1) {
       const uint8_t* p = x + (o - x0);
 #pragma unroll
-      for (int k = 0; k < 8; k++) v |= (uint64_t)p[k] << (8 * k);
+      for (int k = 0; k < 8; k++) v |= (uint64_t)ld_u8<COH>(p + k) << (8 * k);
     } else if (o < padded && !(o >= k1 && o + 8 <= x0) && !(o >= t1 && o + 8 < p1) && !(o >= p1 && o + 8 < padded)) {
       if (o < prefix_len) v |= piece(prefix, 0, prefix_len, o);
       if (key && o + 8 > prefix_len && o < k1) {
         v |= piece(hdr, prefix_len, k0, o);
         v |= piece(key, k0, k1, o);
       }
-      if (o + 8 > x0 && o < x1) v |= piece(x, x0, x1, o);
+      if (o + 8 > x0 && o < x1) v |= piece<COH>(x, x0, x1, o);
       if (o + 8 > x1 && o < t1) v |= x1 >= o ? (uint64_t)trailer << (8 * (uint32_t)(x1 - o)) : (uint64_t)trailer >> (8 * (uint32_t)(o - x1));
       if (has_pad1 && p1 - 1 >= o && p1 - 1 < o + 8) v |= 0x80ull << (8 * (uint32_t)(p1 - 1 - o));
       if (has_pad && padded - 1 >= o && padded - 1 < o + 8) v |= 0x80ull << (8 * (uint32_t)(padded - 1 - o));
@@ -206,7 +227,8 @@ struct SpongeGeom {
 // =====================================================================================================
 // CHAIN: the item may start from / stop at a handed-over state (rank = its slot in the hand-off arrays); the plain
 // kernels instantiate CHAIN = false and compile to what they were.
-template <int LANES, bool CHAIN = false>
+// COH: the message was written earlier in this launch (dependent job): see ld_u8.
+template <int LANES, bool CHAIN = false, bool COH = false>
 __device__ __forceinline__ void sponge_item(const SpongeJob& J, uint64_t i, uint64_t rank = 0) {
   SpongeGeom g;
   g.init(J, i);
@@ -248,7 +270,7 @@ __device__ __forceinline__ void sponge_item(const SpongeJob& J, uint64_t i, uint
     const uint64_t s = b * STRIDE;
     uint64_t blk[LANES];
 #pragma unroll 1
-    for (int j = 0; j < LANES; j++) blk[j] = g.lane(s + 8ull * j);
+    for (int j = 0; j < LANES; j++) blk[j] = g.template lane<COH>(s + 8ull * j);
 #pragma unroll
     for (int j = 0; j < LANES; j++) {
       a[j].lo ^= (uint32_t)blk[j];
@@ -276,7 +298,7 @@ __device__ __forceinline__ void sponge_item(const SpongeJob& J, uint64_t i, uint
     uint2 cur[LANES];
     if (has_fast) {
 #pragma unroll
-      for (int j = 0; j < LANES; j++) cur[j] = __ldg(q + j);
+      for (int j = 0; j < LANES; j++) cur[j] = ld_lane<COH>(q + j);
     }
 #pragma unroll 1
     for (uint64_t b = fb0; b < fb1; b++) {
@@ -284,7 +306,7 @@ __device__ __forceinline__ void sponge_item(const SpongeJob& J, uint64_t i, uint
       uint2 nxt[LANES];
       if (b + 1 < fb1) {
 #pragma unroll
-        for (int j = 0; j < LANES; j++) nxt[j] = __ldg(q + j);
+        for (int j = 0; j < LANES; j++) nxt[j] = ld_lane<COH>(q + j);
       }
 #pragma unroll
       for (int j = 0; j < LANES; j++) {
@@ -302,9 +324,9 @@ __device__ __forceinline__ void sponge_item(const SpongeJob& J, uint64_t i, uint
     uint32_t cw[2 * LANES + 1];
     if (has_fast) {
 #pragma unroll
-      for (int j = 0; j < 2 * LANES; j++) cw[j] = __ldg(q + j);
+      for (int j = 0; j < 2 * LANES; j++) cw[j] = ld_word<COH>(q + j);
       // the last word is only needed (and only guaranteed readable) when sh != 0
-      cw[2 * LANES] = sh != 0 ? __ldg(q + 2 * LANES) : 0u;
+      cw[2 * LANES] = sh != 0 ? ld_word<COH>(q + 2 * LANES) : 0u;
     }
 #pragma unroll 1
     for (uint64_t b = fb0; b < fb1; b++) {
@@ -312,8 +334,8 @@ __device__ __forceinline__ void sponge_item(const SpongeJob& J, uint64_t i, uint
       uint32_t nw[2 * LANES + 1];
       if (b + 1 < fb1) {
 #pragma unroll
-        for (int j = 0; j < 2 * LANES; j++) nw[j] = __ldg(q + j);
-        nw[2 * LANES] = sh != 0 ? __ldg(q + 2 * LANES) : 0u;
+        for (int j = 0; j < 2 * LANES; j++) nw[j] = ld_word<COH>(q + j);
+        nw[2 * LANES] = sh != 0 ? ld_word<COH>(q + 2 * LANES) : 0u;
       }
 #pragma unroll
       for (int j = 0; j < LANES; j++) {
@@ -649,6 +671,9 @@ struct SpongeChain {
   SpongeJob j[2];
   uint32_t* sync;  // [0] ticket counter, [1 + b] warps of job-0 block b that have stored their states; zeroed before the launch
   uint32_t blocks_per_job;
+  // job 1 reads, as its message, bytes that job 0 wrote for the same item (the two passes of an authenticated
+  // decryption: keystream XOR, then the tag over the plaintext): its message loads go to the L2
+  uint32_t data_dependent;
 };
 template <int LANES>
 __global__ void __launch_bounds__(128, CAPY_SPONGE_MINB) sponge_chain_kernel(const __grid_constant__ SpongeChain C) {
@@ -664,7 +689,10 @@ __global__ void __launch_bounds__(128, CAPY_SPONGE_MINB) sponge_chain_kernel(con
     __threadfence();
   }
   const uint64_t r = (uint64_t)b * 128 + threadIdx.x;
-  if (r < J.n) sponge_item<LANES, true>(J, sponge_rank_item(J, r), r);
+  if (r < J.n) {
+    if (job && C.data_dependent) sponge_item<LANES, true, true>(J, sponge_rank_item(J, r), r);
+    else sponge_item<LANES, true>(J, sponge_rank_item(J, r), r);
+  }
   if (!job) {
     __threadfence();  // this thread's state is visible before the warp reports
     __syncwarp();

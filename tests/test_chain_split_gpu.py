@@ -116,3 +116,53 @@ def test_host_entry_point_with_ragged_keys(engine, oracle):
     s_koff = np.concatenate([[0], np.cumsum(klens[pick])]).astype(np.uint64)
     s_data = data.reshape(n, mlen)[pick].reshape(-1)
     assert np.array_equal(cut[pick], oracle.kmac_xof_batch(s_keys, s_koff, s_data, np.arange(65, dtype=np.uint64) * mlen, 512, b"", 512))
+
+
+def test_open_as_dependent_jobs(engine):
+    """sha3_decrypt (sha3/encryptable.rs:58-83) over 2^16 ragged messages: the keystream pass and the tag pass over the
+    recovered plaintext run as dependent jobs of one launch; same plaintexts and verdicts as two launches, tampered
+    items are caught and get their ciphertext back, and a few items are checked against the Python restatement."""
+    from oracle import ref_sha3 as R
+
+    n = N
+    rnd = np.random.default_rng(31)
+    lens = rnd.integers(0, 700, size=n)
+    lens[:4] = [0, 136, 137, 699]
+    mo = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    msg = rnd.integers(0, 256, size=int(mo[-1]), dtype=np.uint8)
+    pw = rnd.integers(0, 256, size=n * 16, dtype=np.uint8)
+    nonces = rnd.integers(0, 256, size=n * 512, dtype=np.uint8)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    t_msg, t_mo, t_pw, t_po, t_n = t(msg), t(mo), t(pw), t(np.arange(n + 1, dtype=np.int64) * 16), t(nonces)
+    ct = torch.zeros_like(t_msg)
+    tag = torch.zeros(n * 64, dtype=torch.uint8, device="cuda")
+    engine.sponge_encrypt_dev(t_pw, t_po, n * 16, t_n, 512, t_msg, t_mo, 512, ct, tag)
+    torch.cuda.synchronize()
+    for i in (0, 1, 2, 3, n - 1):
+        c_ref, t_ref = R.sha3_encrypt(msg[int(mo[i]):int(mo[i + 1])].tobytes(), pw[16 * i:16 * i + 16].tobytes(), 512,
+                                      nonces[512 * i:512 * i + 512].tobytes())
+        assert ct[int(mo[i]):int(mo[i + 1])].cpu().numpy().tobytes() == c_ref and tag[64 * i:64 * i + 64].cpu().numpy().tobytes() == t_ref
+    bad = [7, n // 2, n - 2]
+    tag2 = tag.clone()
+    for i in bad:
+        tag2[64 * i + 5] ^= 1
+
+    def open_(tg):
+        def run():
+            out = torch.zeros_like(t_msg)
+            ok = torch.zeros(n, dtype=torch.uint8, device="cuda")
+            engine.sponge_decrypt_dev(t_pw, t_po, n * 16, t_n, 512, ct, t_mo, tg, 512, out, ok)
+            torch.cuda.synchronize()
+            return out, ok
+        return run
+
+    (o1, k1), (o2, k2) = _both(open_(tag))
+    assert torch.equal(o1, o2) and torch.equal(k1, k2) and bool(k1.all().item()) and torch.equal(o1, t_msg)
+    (o1, k1), (o2, k2) = _both(open_(tag2))
+    assert torch.equal(o1, o2) and torch.equal(k1, k2)
+    ok = k1.cpu().numpy()
+    assert int(ok.sum()) == n - len(bad) and not ok[bad].any()
+    o = o1.cpu().numpy()
+    c = ct.cpu().numpy()
+    for i in bad:  # restore-on-failure: the ciphertext comes back (encryptable.rs:77-82)
+        assert np.array_equal(o[int(mo[i]):int(mo[i + 1])], c[int(mo[i]):int(mo[i + 1])])
