@@ -628,7 +628,9 @@ def extras(eng, dev, peaks, world, dist, rank):
     out["kmac256_2^16x4KB"] = {
         "GBps": world * n2 * mlen / (ms * 1e-3) / 1e9, "ms_per_step": ms,
         "frac_int_alu": n2 * perms * OPS_PER_PERM / (ms * 1e-3) / peaks["lop3"], "perms_per_msg": perms,
-        "oracle_sample": NS}
+        "oracle_sample": NS,
+        "launch": "sponge_chain_kernel: 2 048 warps on 592 schedulers = 3.46 each, so the chains are cut in two dependent jobs "
+                  "of one launch (6.92 warps per scheduler); CAPY_NO_CHAIN_SPLIT=1 gives the uncut launch"}
 
     # cfg 2, variable-length squeeze: cSHAKE256 and KMACXOF256 with a 4 096-byte output per message (the keystream shape of
     # sha3/encryptable.rs:41), and FIPS 202 SHAKE256 (no reference counterpart) with a 64-byte output
@@ -893,13 +895,14 @@ def extras(eng, dev, peaks, world, dist, rank):
         "note": "encrypt = 1 variable-base + 1 fixed-base scalar mult + 3 KMACs, decrypt = 1 variable-base + 4 KMACs"}
 
     # e2e for the Ed448 half of the metric: host buffers through capy_ed448_fixed_base_batch (H2D 56 B, D2H 112 B per item)
-    n6 = 1 << 18
+    # at cfg 3's size (2^20 scalars: four chunks of 2^18 on the ctx's three streams)
+    n6 = n3
     h_sc = eng.pinned(n6 * 56)
     h_sc[:] = sc[: n6 * 56].cpu().numpy()
     h_pts = eng.pinned(n6 * 112).reshape(n6, 112)
     dt = timed_host(lambda: eng.ed448_fixed_base(h_sc, out=h_pts), 3)
-    assert h_pts[:1].tobytes() == pts[:112].cpu().numpy().tobytes()
-    out["ed448_fixed_base_e2e_2^18"] = {"scalar_mults_per_s": world * n6 / dt, "ms_per_step": dt * 1e3,
+    assert np.array_equal(h_pts[idx3], rows(pts, n3, 112, idx3).reshape(NS, 112)), "cfg 3 e2e != device-resident result"
+    out["ed448_fixed_base_e2e_2^20"] = {"scalar_mults_per_s": world * n6 / dt, "ms_per_step": dt * 1e3,
                                         "h2d_bytes_per_step": n6 * 56, "d2h_bytes_per_step": n6 * 112,
                                         "api": "capy_ed448_fixed_base_batch (pinned host buffers from capy_host_alloc)"}
     eng.set_plan_cache(False)

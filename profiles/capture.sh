@@ -14,9 +14,12 @@ cap() {  # name, kernel regex, skip
 }
 cap sha3_short sha3_short 5
 cap sponge_kmac 'sponge_kernel<' 2
+cap sponge_chain sponge_chain_kernel 1
 cap sponge_ae 'sponge_kernel2' 1
 cap sponge_tiered sponge_tiered 0
 cap fixed_base fixed_base_kernel 1
 cap var_base var_base_kernel 1
 python profiles/summarise_ncu.py $O/prof_${TAG}_*.ncu-rep > $O/${TAG}_ncu_summaries.txt
+# gpurun brings back at most 64 MiB of gpurun_out/: keep the summaries, drop the reports
+rm -f $O/prof_${TAG}_*.ncu-rep
 ls -la $O | tail -20
