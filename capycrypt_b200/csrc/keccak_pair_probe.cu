@@ -103,6 +103,54 @@ __global__ void __launch_bounds__(128) chain_warp25(uint64_t* st, int nperm) {
   if (l < 25) st[(size_t)item * 25 + l] = ((uint64_t)hi << 32) | lo;
 }
 
+// One state per warp again, but the lanes are exchanged through SHARED MEMORY instead of shuffles (an attempt to get under
+// the ~180 clocks per round of the shuffle version: 64-bit LDS fetch both halves of a lane at once, so a round issues
+// 3 STS.64 + 8 LDS.64 instead of 18 SHFL; the three dependent exchange stages per round remain).
+__global__ void __launch_bounds__(128) chain_warp25_smem(uint64_t* st, int nperm) {
+  __shared__ uint2 ex[4][3][32];  // per warp: the lanes, the column parities, the rotated lanes
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int item = t >> 5, w = threadIdx.x >> 5;
+  const int l = threadIdx.x & 31;
+  const int ll = l < 25 ? l : 0;
+  const int x = ll % 5, y = ll / 5;
+  uint64_t v = st[(size_t)item * 25 + ll];
+  uint32_t lo = (uint32_t)v, hi = (uint32_t)(v >> 32);
+  const int c1 = (ll + 5) % 25, c2 = (ll + 10) % 25, c3 = (ll + 15) % 25, c4 = (ll + 20) % 25;
+  const int xm = (x + 4) % 5 + 5 * y, xp = (x + 1) % 5 + 5 * y;
+  const uint32_t rho = RHO25[ll];
+  const uint32_t swap = rho >= 32, m = rho & 31;
+  const int s0 = ((x + 3 * y) % 5) + 5 * x;
+  const int s1 = (((x + 1) % 5 + 3 * y) % 5) + 5 * ((x + 1) % 5);
+  const int s2 = (((x + 2) % 5 + 3 * y) % 5) + 5 * ((x + 2) % 5);
+  const uint32_t is0 = ll == 0 && l == 0 ? 0xffffffffu : 0u;
+  uint2* A = ex[w][0];
+  uint2* C = ex[w][1];
+  uint2* E = ex[w][2];
+  for (int p = 0; p < nperm; p++) {
+#pragma unroll 1
+    for (int r = 0; r < 24; r++) {
+      A[l] = make_uint2(lo, hi);
+      __syncwarp();
+      const uint2 a1 = A[c1], a2 = A[c2], a3 = A[c3], a4 = A[c4];
+      const uint32_t clo = lop_xor3(lop_xor3(lo, a1.x, a2.x), a3.x, a4.x);
+      const uint32_t chi = lop_xor3(lop_xor3(hi, a1.y, a2.y), a3.y, a4.y);
+      C[l] = make_uint2(clo, chi);
+      __syncwarp();
+      const uint2 cm = C[xm], cp = C[xp];
+      const uint32_t tlo = lop_xor3(lo, cm.x, __funnelshift_l(cp.y, cp.x, 1));
+      const uint32_t thi = lop_xor3(hi, cm.y, __funnelshift_l(cp.x, cp.y, 1));
+      const uint32_t alo = swap ? thi : tlo, ahi = swap ? tlo : thi;
+      E[l] = make_uint2(__funnelshift_l(ahi, alo, m), __funnelshift_l(alo, ahi, m));
+      __syncwarp();
+      const uint2 b0 = E[s0], b1 = E[s1], b2 = E[s2];
+      const uint2 rc = KECCAK_RC[r];
+      lo = lop_chi(b0.x, b1.x, b2.x) ^ (rc.x & is0);
+      hi = lop_chi(b0.y, b1.y, b2.y) ^ (rc.y & is0);
+    }
+  }
+  if (l < 25) st[(size_t)item * 25 + l] = ((uint64_t)hi << 32) | lo;
+}
+
 // the same permutation through the WarpKeccak struct the sponge uses, with an early exit in front (what the
 // tiered kernel has) and one XOR per permutation standing in for the absorb
 __global__ void __launch_bounds__(128) chain_warp25_struct(uint64_t* st, int nperm, int n_items, const uint32_t* __restrict__ feed) {
@@ -158,6 +206,22 @@ int main(int argc, char** argv) {
       printf("{\"warps_per_scheduler\": %d, \"warp25_us_per_perm\": %.4f, \"chain_speedup_vs_single\": %.3f, \"warp25_Gperm_s\": %.4f, \"mismatching_lanes\": %zu}\n",
              wps, ms3 * 1e3 / nperm, ms1 / ms3, threads / 32 / (ms3 * 1e-3 / nperm) / 1e9, bad3);
       cudaFree(d3);
+    }
+    {
+      uint64_t* d7; cudaMalloc(&d7, init.size() * 8);
+      cudaMemcpy(d7, init.data(), init.size() * 8, cudaMemcpyHostToDevice);
+      chain_warp25_smem<<<blocks, 128>>>(d7, 2);
+      float ms7;
+      cudaEventRecord(e0); chain_warp25_smem<<<blocks, 128>>>(d7, nperm); cudaEventRecord(e1); cudaEventSynchronize(e1);
+      cudaEventElapsedTime(&ms7, e0, e1);
+      std::vector<uint64_t> r7((size_t)threads * 25), r1c((size_t)threads * 25);
+      cudaMemcpy(r7.data(), d7, r7.size() * 8, cudaMemcpyDeviceToHost);
+      cudaMemcpy(r1c.data(), d1, r1c.size() * 8, cudaMemcpyDeviceToHost);
+      size_t bad7 = 0;
+      for (size_t i = 0; i < (size_t)threads / 32 * 25; i++) bad7 += r1c[i] != r7[i];
+      printf("{\"warps_per_scheduler\": %d, \"warp25_shared_memory_exchange_us_per_perm\": %.4f, \"mismatching_lanes\": %zu}\n", wps,
+             ms7 * 1e3 / nperm, bad7);
+      cudaFree(d7);
     }
     {
       uint64_t* d4; cudaMalloc(&d4, init.size() * 8);
