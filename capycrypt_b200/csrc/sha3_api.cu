@@ -557,6 +557,10 @@ static int launch_sponge(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t stream, int 
   }
 }
 
+// chain cutting of uniform batches (defined with the cSHAKE / KMAC launchers below)
+static bool chain_cut(int sm_count, uint64_t n, uint64_t absorb_blocks, uint64_t squeeze_extra, uint64_t* cut);
+static int launch_sponge_chain(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t stream, int lanes, const SpongeJob& J, uint64_t cut);
+
 static SpongeJob empty_job() {
   SpongeJob J;
   memset(&J, 0, sizeof J);
@@ -614,8 +618,10 @@ static int launch_sha3(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t stream, int d,
     CAPY_CUDA(ctx, cudaGetLastError());
     return CAPY_OK;
   }
+  uint64_t cut = 0;
+  const bool cut_fixed = !off && chain_cut(dc.sm_count, n, msg_len / rate + 1, 0, &cut);  // long equal messages, uneven fill
   // the uniform kernel stores 4-byte granules (28- and 48-byte digests) and reads whole 8-byte words
-  if (!off && (reinterpret_cast<uintptr_t>(data) & 7u) == 0 && (stride & 7u) == 0 &&
+  if (!off && !cut_fixed && (reinterpret_cast<uintptr_t>(data) & 7u) == 0 && (stride & 7u) == 0 &&
       (reinterpret_cast<uintptr_t>(out) & 3u) == 0 && (tail_readable || (msg_len & 7u) == 0)) {
     const uint32_t suffix = (msg_len % 136u == 135u) ? 0x86u : 0x06u;  // shake_functions.rs:25-29 (Q2)
     const unsigned block = 128, grid = grid_for(n, block);
@@ -648,6 +654,9 @@ static int launch_sha3(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t stream, int d,
     if (rc) return rc;
   }
   J.order = plan.order;
+  if (cut_fixed) return launch_sponge_chain(ctx, dc, stream, lanes, J, cut);
+  if (off && !plan.order && plan.uniform_blocks && chain_cut(dc.sm_count, n, plan.uniform_blocks, 0, &cut))
+    return launch_sponge_chain(ctx, dc, stream, lanes, J, cut);
   return launch_sponge(ctx, dc, stream, lanes, J, plan);
 }
 
@@ -800,7 +809,10 @@ static int launch_chain_jobs(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t stream, 
   C.blocks_per_job = nb;
   C.data_dependent = data_dependent ? 1u : 0u;
   switch (lanes) {
+    case 9: return launch_chain_t<9>(ctx, stream, C, 2 * nb);
+    case 13: return launch_chain_t<13>(ctx, stream, C, 2 * nb);
     case 17: return launch_chain_t<17>(ctx, stream, C, 2 * nb);
+    case 18: return launch_chain_t<18>(ctx, stream, C, 2 * nb);
     case 19: return launch_chain_t<19>(ctx, stream, C, 2 * nb);
     case 21: return launch_chain_t<21>(ctx, stream, C, 2 * nb);
     default: return CAPY_ERR_BAD_ARG;

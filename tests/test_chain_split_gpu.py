@@ -166,3 +166,35 @@ def test_open_as_dependent_jobs(engine):
     c = ct.cpu().numpy()
     for i in bad:  # restore-on-failure: the ciphertext comes back (encryptable.rs:77-82)
         assert np.array_equal(o[int(mo[i]):int(mo[i + 1])], c[int(mo[i]):int(mo[i + 1])])
+
+
+@pytest.mark.parametrize("d,mlen", [(256, 2000), (512, 1000), (224, 2015), (384, 1400)])
+def test_sha3_equal_long_messages(engine, oracle, d, mlen):
+    """compute_sha3_hash (sha3/hashable.rs:19-21) over 2^16 equal messages of a dozen blocks or more: fixed-length entry
+    point and offsets entry point, cut and uncut, against the oracle (the quirk lengths of Q1 / Q2 included via mlen)"""
+    rate = {224: 144, 256: 136, 384: 104, 512: 72}[d]
+    assert _would_cut(engine, mlen // rate + 1)
+    g = torch.Generator(device="cuda")
+    g.manual_seed(3 * d + mlen)
+    data = torch.randint(0, 256, (N * mlen,), dtype=torch.uint8, device="cuda", generator=g)
+    off = torch.arange(N + 1, dtype=torch.int64, device="cuda") * mlen
+
+    def fixed():
+        out = torch.zeros(N * (d // 8), dtype=torch.uint8, device="cuda")
+        engine.sha3_fixed_dev(data, mlen, mlen, N, d, out)
+        torch.cuda.synchronize()
+        return out
+
+    def ragged():
+        out = torch.zeros(N * (d // 8), dtype=torch.uint8, device="cuda")
+        engine.sha3_dev(data, off, d, out)
+        torch.cuda.synchronize()
+        return out
+
+    f_cut, f_plain = _both(fixed)
+    r_cut, r_plain = _both(ragged)
+    assert torch.equal(f_cut, f_plain) and torch.equal(r_cut, r_plain) and torch.equal(f_cut, r_cut)
+    pick = np.sort(np.random.default_rng(d).choice(N, size=64, replace=False))
+    idx = torch.from_numpy(pick).cuda()
+    want = oracle.sha3_batch(data.view(N, mlen)[idx].cpu().numpy().reshape(-1), np.arange(65, dtype=np.uint64) * mlen, d, threads=0)
+    assert np.array_equal(f_cut.view(N, d // 8)[idx].cpu().numpy(), want)
