@@ -843,7 +843,7 @@ def extras(eng, dev, peaks, world, dist, rank):
     eng.ed448_sign_dev(pw, pw_off, msg, msg_off, 512, h, z)  # h, z back to the 256-byte messages for what follows
 
     # ---- "next" rows N2 / N3: sponge AE over the cfg-2 shape (2^16 x 4 KB: the tag pass and the keystream pass
-    # of the seal are one launch) and ECDHIES over 2^17 x 256 B, device-resident ------------------------------------
+    # of the seal are one launch) and ECDHIES over 2^18 x 256 B, device-resident ------------------------------------
     from oracle import ref_sha3
 
     nonces = rnd(n2 * 512)
@@ -872,7 +872,7 @@ def extras(eng, dev, peaks, world, dist, rank):
 
     from oracle import ref_ed448
 
-    n5 = 1 << 17
+    n5 = n4  # 2^18 like cfg 4 (1 024 blocks of var_base_kernel = 6.92 per SM; 2^17 would be 3.46: a quarter wave idle)
     k_rand = rnd(n5 * 56)
     m5 = msg[: n5 * 256]
     m5_off = msg_off[: n5 + 1]
@@ -889,7 +889,7 @@ def extras(eng, dev, peaks, world, dist, rank):
                                                     k_rand[i * 56:(i + 1) * 56].cpu().numpy().tobytes())
         assert ct5[i * 256:(i + 1) * 256].cpu().numpy().tobytes() == c_ref and tag5[i * 56:(i + 1) * 56].cpu().numpy().tobytes() == t_ref
         assert zpt[i * 112:(i + 1) * 112].cpu().numpy().tobytes() == ref_ed448.point_to_bytes(z_ref), "key_encrypt != oracle"
-    out["ed448_ecdhies_2^17x256B"] = {
+    out["ed448_ecdhies_2^18x256B"] = {
         "key_encrypts_per_s": world * n5 / (ms_e * 1e-3), "key_decrypts_per_s": world * n5 / (ms_d * 1e-3),
         "ms_encrypt": ms_e, "ms_decrypt": ms_d,
         "note": "encrypt = 1 variable-base + 1 fixed-base scalar mult + 3 KMACs, decrypt = 1 variable-base + 4 KMACs"}
