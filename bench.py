@@ -463,6 +463,16 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     assert h_out[:DIGEST].tobytes() == hashlib.sha3_256(m0).digest()
+    # the same call from ordinary (pageable) memory -- what a caller gets that hands over a Vec / numpy array instead of
+    # packing into a capy_host_alloc buffer: the driver stages such copies through its own pinned buffers
+    p_in, p_out = np.array(h_in), np.zeros((N_MSGS, DIGEST), np.uint8)
+    eng.sha3_fixed(p_in, MSG_LEN, MSG_LEN, N_MSGS, 256, out=p_out)
+    t0 = time.perf_counter()
+    for _ in range(5):
+        eng.sha3_fixed(p_in, MSG_LEN, MSG_LEN, N_MSGS, 256, out=p_out)
+    pageable_s = (time.perf_counter() - t0) / 5
+    assert np.array_equal(p_out, h_out2d)
+    del p_in, p_out
     # the denominator of the end-to-end number: the same bytes, the same pinned buffers, every rank at the same time,
     # plain cudaMemcpyAsync in both directions and no kernel (capy_copy_probe)
     if dist:
@@ -481,7 +491,8 @@ def main():
            "link_ceiling_GBps": link_ceiling, "link_ms_per_step": link_ms, "frac_of_link": e2e_val / link_ceiling,
            "link_probe": "capy_copy_probe: 64 MiB H2D + 32 MiB D2H per rank from the same pinned buffers, both directions "
                          "overlapped, all ranks concurrently, no kernel (max over ranks)",
-           "host_numa_binding": numa}
+           "host_numa_binding": numa,
+           "pageable_buffers_GBps_this_rank": N_MSGS * MSG_LEN / pageable_s / 1e9}
 
     # ---- roofline of the dominant kernel (sha3_short_kernel<17, 8>: one launch per step) ----
     ops = N_MSGS * OPS_PER_PERM

@@ -318,7 +318,10 @@ static int dev_key_decrypt(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t st, int d,
 static int h2d_fixed(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t st, int slot, const uint8_t* src, size_t bytes, uint8_t** out) {
   uint8_t* d = (uint8_t*)scratch_get(dc, slot, bytes + 16);
   if (!d) return CAPY_ERR_OOM;
-  if (bytes) CAPY_CUDA(ctx, cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, st));
+  if (bytes) {
+    const int rc = copy_in(ctx, dc, st, slot, d, src, bytes);
+    if (rc) return rc;
+  }
   *out = d;
   return CAPY_OK;
 }
@@ -337,10 +340,10 @@ static int stage_out(DeviceCtx& dc, int slot, const uint64_t* off, uint64_t i0, 
   o->d_base = reinterpret_cast<uint8_t*>(reinterpret_cast<uintptr_t>(o->d_raw) - (uintptr_t)o->a0);
   return CAPY_OK;
 }
-static int fetch_out(capy_ctx* ctx, cudaStream_t st, const StagedOut& o, const uint64_t* off, uint64_t i0, uint64_t i1,
-                     uint8_t* host) {
+static int fetch_out(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t st, const StagedOut& o, const uint64_t* off, uint64_t i0,
+                     uint64_t i1, uint8_t* host) {
   const uint64_t b0 = off[i0], b1 = off[i1];
-  if (b1 > b0) CAPY_CUDA(ctx, cudaMemcpyAsync(host + b0, o.d_base + b0, (size_t)(b1 - b0), cudaMemcpyDeviceToHost, st));
+  if (b1 > b0) return copy_out(ctx, dc, st, SA_H0 + 5, host + b0, o.d_base + b0, (size_t)(b1 - b0));
   return CAPY_OK;
 }
 
@@ -413,7 +416,7 @@ int capy_sponge_encrypt_batch(capy_ctx* ctx, int d_bits, int variant, const uint
     rc = dev_sponge_encrypt(ctx, dc, st, d_bits, variant, sp.d_base, sp.d_off, pw_off[sh.i1] - pw_off[sh.i0], d_nonce,
                             nonce_len, sm.d_base, sm.d_off, cnt, so.d_base, d_tag);
     if (rc) return rc;
-    rc = fetch_out(ctx, st, so, msg_off, sh.i0, sh.i1, ct);
+    rc = fetch_out(ctx, dc, st, so, msg_off, sh.i0, sh.i1, ct);
     if (rc) return rc;
     CAPY_CUDA(ctx, cudaMemcpyAsync(tag64 + 64 * sh.i0, d_tag, cnt * 64, cudaMemcpyDeviceToHost, st));
     CAPY_CUDA(ctx, cudaStreamSynchronize(st));
@@ -450,7 +453,7 @@ int capy_sponge_decrypt_batch(capy_ctx* ctx, int d_bits, int variant, const uint
     rc = dev_sponge_decrypt(ctx, dc, st, d_bits, variant, sp.d_base, sp.d_off, pw_off[sh.i1] - pw_off[sh.i0], d_nonce,
                             nonce_len, sc.d_base, sc.d_off, d_tag, cnt, so.d_base, d_ok);
     if (rc) return rc;
-    rc = fetch_out(ctx, st, so, ct_off, sh.i0, sh.i1, out);
+    rc = fetch_out(ctx, dc, st, so, ct_off, sh.i0, sh.i1, out);
     if (rc) return rc;
     CAPY_CUDA(ctx, cudaMemcpyAsync(ok + sh.i0, d_ok, cnt, cudaMemcpyDeviceToHost, st));
     CAPY_CUDA(ctx, cudaStreamSynchronize(st));
@@ -508,7 +511,7 @@ int capy_ed448_key_encrypt_batch(capy_ctx* ctx, int d_bits, const uint8_t* pub_x
     CAPY_CUDA(ctx, cudaMemsetAsync(d_flag, 0, sizeof(int), st));
     rc = dev_key_encrypt(ctx, dc, st, d_bits, d_pub, d_k, sm.d_base, sm.d_off, cnt, so.d_base, d_tag, d_z, d_flag);
     if (rc) return rc;
-    rc = fetch_out(ctx, st, so, msg_off, sh.i0, sh.i1, ct);
+    rc = fetch_out(ctx, dc, st, so, msg_off, sh.i0, sh.i1, ct);
     if (rc) return rc;
     CAPY_CUDA(ctx, cudaMemcpyAsync(tag56 + 56 * sh.i0, d_tag, cnt * 56, cudaMemcpyDeviceToHost, st));
     CAPY_CUDA(ctx, cudaMemcpyAsync(z_xy112 + 112 * sh.i0, d_z, cnt * 112, cudaMemcpyDeviceToHost, st));
@@ -551,7 +554,7 @@ int capy_ed448_key_decrypt_batch(capy_ctx* ctx, int d_bits, const uint8_t* pws, 
     rc = dev_key_decrypt(ctx, dc, st, d_bits, sp.d_base, sp.d_off, d_z, sc.d_base, sc.d_off, d_tag, cnt, so.d_base, d_ok,
                          d_flag);
     if (rc) return rc;
-    rc = fetch_out(ctx, st, so, ct_off, sh.i0, sh.i1, out);
+    rc = fetch_out(ctx, dc, st, so, ct_off, sh.i0, sh.i1, out);
     if (rc) return rc;
     CAPY_CUDA(ctx, cudaMemcpyAsync(ok + sh.i0, d_ok, cnt, cudaMemcpyDeviceToHost, st));
     return read_flag(ctx, st, d_flag, &flags[dc.index]);

@@ -1,5 +1,7 @@
 // ctx.cu -- context, streams, scratch memory and error plumbing of libcapycrypt_gpu.
+#include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "internal.h"
@@ -71,6 +73,171 @@ void DeviceWorker::loop(int dev) {
     }
     f();
   }
+}
+
+// ---- staging of pageable host buffers (internal.h) --------------------------------------------------------------------
+CopyPool::CopyPool(int helpers) {
+  for (int k = 0; k < helpers; k++) th_.emplace_back([this] { loop(); });
+}
+CopyPool::~CopyPool() {
+  {
+    std::lock_guard<std::mutex> lk(m_);
+    stop_ = true;
+  }
+  cv_.notify_all();
+  for (auto& t : th_)
+    if (t.joinable()) t.join();
+}
+void CopyPool::loop() {
+  uint64_t seen = 0;
+  for (;;) {
+    std::unique_lock<std::mutex> lk(m_);
+    cv_.wait(lk, [&] { return stop_ || gen_ != seen; });
+    if (stop_) return;
+    seen = gen_;
+    while (next_ < slices_) {
+      const int k = next_++;
+      const size_t a = (size_t)k * slice_, b = std::min(bytes_, a + slice_);
+      lk.unlock();
+      if (b > a) memcpy(dst_ + a, src_ + a, b - a);
+      lk.lock();
+      if (--left_ == 0) done_cv_.notify_all();
+    }
+  }
+}
+void CopyPool::copy(void* dst, const void* src, size_t bytes) {
+  if (bytes < (1u << 20) || th_.empty()) {
+    memcpy(dst, src, bytes);
+    return;
+  }
+  std::unique_lock<std::mutex> lk(m_);
+  dst_ = (uint8_t*)dst;
+  src_ = (const uint8_t*)src;
+  bytes_ = bytes;
+  slices_ = (int)th_.size() + 1;
+  slice_ = ((bytes + slices_ - 1) / slices_ + 4095) & ~(size_t)4095;
+  next_ = 0;
+  left_ = slices_;
+  gen_++;
+  cv_.notify_all();
+  while (next_ < slices_) {  // the caller takes slices too
+    const int k = next_++;
+    const size_t a = (size_t)k * slice_, b = std::min(bytes_, a + slice_);
+    lk.unlock();
+    if (b > a) memcpy(dst_ + a, src_ + a, b - a);
+    lk.lock();
+    --left_;
+  }
+  done_cv_.wait(lk, [&] { return left_ == 0; });
+}
+
+static bool host_is_pageable(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return true;
+  }
+  return a.type == cudaMemoryTypeUnregistered;
+}
+
+static int stage_ready(capy_ctx* ctx, DeviceCtx& dc, StageSlot& ss) {
+  if (!ss.p) {
+    void* p = nullptr;
+    CAPY_CUDA(ctx, cudaHostAlloc(&p, 2 * kStagePiece, cudaHostAllocPortable));
+    ss.p = (uint8_t*)p;
+    for (int h = 0; h < 2; h++) CAPY_CUDA(ctx, cudaEventCreateWithFlags(&ss.ev[h], cudaEventDisableTiming));
+  }
+  if (!dc.copy_pool) {
+    // one memcpy thread moves ~6-8 GB/s on this class of host; the link takes 52: up to seven helpers beside the caller,
+    // fewer on small hosts (CAPY_COPY_THREADS overrides)
+    int helpers = (int)std::thread::hardware_concurrency() / 2 - 1;
+    if (const char* e = getenv("CAPY_COPY_THREADS")) helpers = atoi(e) - 1;
+    helpers = std::max(0, std::min(helpers, 7));
+    dc.copy_pool.reset(new CopyPool(helpers));
+  }
+  return CAPY_OK;
+}
+
+// the half must be free: its last DMA has finished and, for a device-to-host half, its bytes have been handed over
+static int stage_settle(capy_ctx* ctx, DeviceCtx& dc, StageSlot& ss, int h) {
+  if (!ss.pending[h]) return CAPY_OK;
+  CAPY_CUDA(ctx, cudaEventSynchronize(ss.ev[h]));
+  if (ss.drain_dst[h]) {
+    dc.copy_pool->copy(ss.drain_dst[h], ss.p + (size_t)h * kStagePiece, ss.drain_bytes[h]);
+    ss.drain_dst[h] = nullptr;
+  }
+  ss.pending[h] = false;
+  return CAPY_OK;
+}
+
+int copy_in(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t st, int slot, void* d_dst, const void* h_src, size_t bytes) {
+  if (bytes == 0) return CAPY_OK;
+  if (bytes < kStageMinBytes || slot < 0 || slot >= kNumScratch || !host_is_pageable(h_src)) {
+    CAPY_CUDA(ctx, cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, st));
+    return CAPY_OK;
+  }
+  StageSlot& ss = dc.stage[slot];
+  int rc = stage_ready(ctx, dc, ss);
+  if (rc) return rc;
+  for (size_t at = 0; at < bytes; at += kStagePiece) {
+    const size_t len = std::min(kStagePiece, bytes - at);
+    const int h = ss.next;
+    ss.next ^= 1;
+    rc = stage_settle(ctx, dc, ss, h);
+    if (rc) return rc;
+    uint8_t* half = ss.p + (size_t)h * kStagePiece;
+    dc.copy_pool->copy(half, (const uint8_t*)h_src + at, len);
+    CAPY_CUDA(ctx, cudaMemcpyAsync((uint8_t*)d_dst + at, half, len, cudaMemcpyHostToDevice, st));
+    CAPY_CUDA(ctx, cudaEventRecord(ss.ev[h], st));
+    ss.pending[h] = true;
+  }
+  return CAPY_OK;
+}
+
+int copy_out(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t st, int slot, void* h_dst, const void* d_src, size_t bytes) {
+  if (bytes == 0) return CAPY_OK;
+  if (bytes < kStageMinBytes || slot < 0 || slot >= kNumScratch || !host_is_pageable(h_dst)) {
+    CAPY_CUDA(ctx, cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, st));
+    return CAPY_OK;
+  }
+  StageSlot& ss = dc.stage[slot];
+  int rc = stage_ready(ctx, dc, ss);
+  if (rc) return rc;
+  for (size_t at = 0; at < bytes; at += kStagePiece) {
+    const size_t len = std::min(kStagePiece, bytes - at);
+    const int h = ss.next;
+    ss.next ^= 1;
+    rc = stage_settle(ctx, dc, ss, h);
+    if (rc) return rc;
+    uint8_t* half = ss.p + (size_t)h * kStagePiece;
+    CAPY_CUDA(ctx, cudaMemcpyAsync(half, (const uint8_t*)d_src + at, len, cudaMemcpyDeviceToHost, st));
+    CAPY_CUDA(ctx, cudaEventRecord(ss.ev[h], st));
+    ss.pending[h] = true;
+    ss.drain_dst[h] = (uint8_t*)h_dst + at;
+    ss.drain_bytes[h] = len;
+  }
+  return CAPY_OK;
+}
+
+int stage_drain(capy_ctx* ctx, DeviceCtx& dc) {
+  int rc = CAPY_OK;
+  for (StageSlot& ss : dc.stage)
+    for (int h = 0; h < 2; h++)
+      if (ss.pending[h]) {
+        const int r = stage_settle(ctx, dc, ss, h);
+        if (r && !rc) rc = r;
+      }
+  return rc;
+}
+
+void stage_free(DeviceCtx& dc) {
+  for (StageSlot& ss : dc.stage) {
+    for (int h = 0; h < 2; h++)
+      if (ss.ev[h]) cudaEventDestroy(ss.ev[h]);
+    if (ss.p) cudaFreeHost(ss.p);
+    ss = StageSlot();
+  }
+  dc.copy_pool.reset();
 }
 
 void plan_cache_clear(DeviceCtx& dc) {
@@ -162,6 +329,7 @@ void capy_gpu_destroy(capy_ctx* ctx) {
       if (kv.second.d_prefix) cudaFree(kv.second.d_prefix);
     }
     ed448_tables_free(dc);
+    stage_free(dc);
   }
   delete ctx;
 }

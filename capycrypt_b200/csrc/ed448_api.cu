@@ -320,7 +320,10 @@ struct HostIn {
 static int h2d(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t st, int slot, const void* src, size_t bytes, uint8_t** out) {
   uint8_t* d = (uint8_t*)scratch_get(dc, slot, bytes + 16);
   if (!d) return CAPY_ERR_OOM;
-  if (bytes) CAPY_CUDA(ctx, cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, st));
+  if (bytes) {
+    const int rc = copy_in(ctx, dc, st, slot, d, src, bytes);
+    if (rc) return rc;
+  }
   *out = d;
   return CAPY_OK;
 }
@@ -425,8 +428,7 @@ int capy_ed448_fixed_base_batch(capy_ctx* ctx, const uint8_t* scalars_be56, uint
       if (!d_out) return CAPY_ERR_OOM;
       rc = dev_fixed_base(ctx, dc, st, d_sc, cnt, d_out);
       if (rc) return rc;
-      CAPY_CUDA(ctx, cudaMemcpyAsync(out_xy112 + 112 * ch.i0, d_out, cnt * 112, cudaMemcpyDeviceToHost, st));
-      return CAPY_OK;
+      return copy_out(ctx, dc, st, ed_slot(SL_H_IN0 + 1, ss), out_xy112 + 112 * ch.i0, d_out, cnt * 112);
     });
   });
 }
@@ -449,8 +451,7 @@ int capy_ed448_var_base_batch(capy_ctx* ctx, const uint8_t* scalars_be56, const 
       if (!d_out) return CAPY_ERR_OOM;
       rc = dev_var_base(ctx, dc, st, d_sc, d_pt, cnt, d_out, d_flag);
       if (rc) return rc;
-      CAPY_CUDA(ctx, cudaMemcpyAsync(out_xy112 + 112 * ch.i0, d_out, cnt * 112, cudaMemcpyDeviceToHost, st));
-      return CAPY_OK;
+      return copy_out(ctx, dc, st, ed_slot(SL_H_IN0 + 2, ss), out_xy112 + 112 * ch.i0, d_out, cnt * 112);
     });
   });
   if (rc) return rc;
@@ -475,8 +476,7 @@ int capy_ed448_keygen_batch(capy_ctx* ctx, int d_bits, const uint8_t* pws, const
       if (!d_out) return CAPY_ERR_OOM;
       rc = dev_keygen(ctx, dc, st, d_bits, sp.d_base, sp.d_off, cnt, d_out);
       if (rc) return rc;
-      CAPY_CUDA(ctx, cudaMemcpyAsync(out_xy112 + 112 * ch.i0, d_out, cnt * 112, cudaMemcpyDeviceToHost, st));
-      return CAPY_OK;
+      return copy_out(ctx, dc, st, ed_slot(SL_H_IN0 + 2, ss), out_xy112 + 112 * ch.i0, d_out, cnt * 112);
     });
   });
 }
@@ -500,9 +500,9 @@ int capy_ed448_sign_batch(capy_ctx* ctx, int d_bits, const uint8_t* pws, const u
       if (!d_h || !d_z) return CAPY_ERR_OOM;
       rc = dev_sign(ctx, dc, st, d_bits, sp.d_base, sp.d_off, sm.d_base, sm.d_off, cnt, d_h, d_z);
       if (rc) return rc;
-      CAPY_CUDA(ctx, cudaMemcpyAsync(h56 + 56 * ch.i0, d_h, cnt * 56, cudaMemcpyDeviceToHost, st));
-      CAPY_CUDA(ctx, cudaMemcpyAsync(z_be56 + 56 * ch.i0, d_z, cnt * 56, cudaMemcpyDeviceToHost, st));
-      return CAPY_OK;
+      rc = copy_out(ctx, dc, st, ed_slot(SL_H_IN0 + 4, ss), h56 + 56 * ch.i0, d_h, cnt * 56);
+      if (rc) return rc;
+      return copy_out(ctx, dc, st, ed_slot(SL_H_IN0 + 5, ss), z_be56 + 56 * ch.i0, d_z, cnt * 56);
     });
   });
 }
@@ -531,8 +531,7 @@ int capy_ed448_verify_batch(capy_ctx* ctx, int d_bits, const uint8_t* pub_xy112,
       if (!d_ok) return CAPY_ERR_OOM;
       rc = dev_verify(ctx, dc, st, d_bits, d_pub, sm.d_base, sm.d_off, d_h, d_z, cnt, d_ok, d_flag);
       if (rc) return rc;
-      CAPY_CUDA(ctx, cudaMemcpyAsync(ok + ch.i0, d_ok, cnt, cudaMemcpyDeviceToHost, st));
-      return CAPY_OK;
+      return copy_out(ctx, dc, st, ed_slot(SL_H_IN0 + 5, ss), ok + ch.i0, d_ok, cnt);
     });
   });
   if (rc) return rc;
@@ -567,7 +566,8 @@ int capy_ed448_ecdh_batch(capy_ctx* ctx, const uint8_t* k_rand56, const uint8_t*
       any_bad_kernel<<<grid_for(cnt, 256), 256, 0, st>>>(bad, d_flag, cnt);
       ctx->launches++;
       CAPY_CUDA(ctx, cudaGetLastError());
-      CAPY_CUDA(ctx, cudaMemcpyAsync(wx56 + 56 * ch.i0, d_wx, cnt * 56, cudaMemcpyDeviceToHost, st));
+      rc = copy_out(ctx, dc, st, ed_slot(SL_H_IN0 + 2, ss), wx56 + 56 * ch.i0, d_wx, cnt * 56);
+      if (rc) return rc;
       if (z_xy112) {  // Z = [k]G (:38)
         uint32_t* kw = (uint32_t*)scratch_get(dc, ed_slot(SL_KWORDS, ss), cnt * 56);
         uint8_t* d_z = (uint8_t*)scratch_get(dc, ed_slot(SL_H_IN0 + 3, ss), cnt * 112);
@@ -578,7 +578,8 @@ int capy_ed448_ecdh_batch(capy_ctx* ctx, const uint8_t* k_rand56, const uint8_t*
         if (rc) return rc;
         rc = launch_to_affine(ctx, st, proj, cnt, 0, nullptr, d_z);
         if (rc) return rc;
-        CAPY_CUDA(ctx, cudaMemcpyAsync(z_xy112 + 112 * ch.i0, d_z, cnt * 112, cudaMemcpyDeviceToHost, st));
+        rc = copy_out(ctx, dc, st, ed_slot(SL_H_IN0 + 3, ss), z_xy112 + 112 * ch.i0, d_z, cnt * 112);
+        if (rc) return rc;
       }
       return CAPY_OK;
     });

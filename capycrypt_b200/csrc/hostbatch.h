@@ -140,7 +140,9 @@ inline int for_each_device(capy_ctx* ctx, const std::vector<Range>& shards, F&& 
     std::lock_guard<std::mutex> lk(*dc.mu);
     DeviceGuard g(dc.dev);
     HostOffScope hs(dc);
-    return fn(dc, shards[0]);
+    const int rc = fn(dc, shards[0]);
+    const int rd = stage_drain(ctx, dc);  // staged device-to-host copies: hand the bytes to the caller's buffers
+    return rc ? rc : rd;
   }
   std::vector<int> rcs(shards.size(), CAPY_OK);
   std::mutex m;
@@ -153,6 +155,8 @@ inline int for_each_device(capy_ctx* ctx, const std::vector<Range>& shards, F&& 
         std::lock_guard<std::mutex> lk(*ctx->devs[k].mu);
         HostOffScope hs(ctx->devs[k]);
         rcs[k] = fn(ctx->devs[k], shards[k]);
+        const int rd = stage_drain(ctx, ctx->devs[k]);
+        if (!rcs[k]) rcs[k] = rd;
       }
       std::lock_guard<std::mutex> lk(m);
       if (--pending == 0) cv.notify_one();
@@ -180,8 +184,14 @@ inline int stage_packed(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t st, int slot_
   uint8_t* d_data = (uint8_t*)scratch_get(dc, slot_data, nbytes + 16);
   uint64_t* d_off = (uint64_t*)scratch_get(dc, slot_off, (size_t)(i1 - i0 + 1) * 8);
   if (!d_data || !d_off) return CAPY_ERR_OOM;
-  if (nbytes) CAPY_CUDA(ctx, cudaMemcpyAsync(d_data, data + a0, nbytes, cudaMemcpyHostToDevice, st));
-  CAPY_CUDA(ctx, cudaMemcpyAsync(d_off, off + i0, (size_t)(i1 - i0 + 1) * 8, cudaMemcpyHostToDevice, st));
+  if (nbytes) {
+    const int rc = copy_in(ctx, dc, st, slot_data, d_data, data + a0, nbytes);
+    if (rc) return rc;
+  }
+  {
+    const int rc = copy_in(ctx, dc, st, slot_off, d_off, off + i0, (size_t)(i1 - i0 + 1) * 8);
+    if (rc) return rc;
+  }
   out->d_base = reinterpret_cast<const uint8_t*>(reinterpret_cast<uintptr_t>(d_data) - (uintptr_t)a0);
   out->d_off = d_off;
   host_off_register(dc, d_off, off + i0, i1 - i0 + 1);  // plan_ragged plans from the host copy: no device round trip

@@ -79,6 +79,43 @@ class DeviceWorker {
 
 struct Ed448Tables;  // defined in ed448_api.cu
 
+// ---- staging of pageable host memory ---------------------------------------------------------------------------------
+// A copy between the device and ordinary (pageable) host memory goes through the driver's own bounce buffers on the
+// calling thread: 8.9 GB/s for the 64 MiB + 32 MiB of BASELINE config 1 against 46.7 GB/s from page-locked buffers.  Host
+// entry points therefore stage large pageable buffers themselves: a few host threads copy a piece into (out of) a
+// page-locked double buffer while the DMA of the previous piece runs.  Buffers from capy_host_alloc skip all of this.
+constexpr size_t kStagePiece = 8ull << 20;      // bytes per staging half
+constexpr size_t kStageMinBytes = 256ull << 10;  // smaller copies are left to the driver
+struct StageSlot {
+  uint8_t* p = nullptr;  // 2 x kStagePiece, page-locked
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  bool pending[2] = {false, false};
+  // device-to-host: where the bytes of a half go once its copy has arrived
+  void* drain_dst[2] = {nullptr, nullptr};
+  size_t drain_bytes[2] = {0, 0};
+  int next = 0;
+};
+
+// a few persistent helper threads that split one memcpy between them (and the caller)
+class CopyPool {
+ public:
+  explicit CopyPool(int helpers);
+  ~CopyPool();
+  void copy(void* dst, const void* src, size_t bytes);
+
+ private:
+  void loop();
+  std::mutex m_;
+  std::condition_variable cv_, done_cv_;
+  std::vector<std::thread> th_;
+  uint8_t* dst_ = nullptr;
+  const uint8_t* src_ = nullptr;
+  size_t bytes_ = 0, slice_ = 0;
+  int next_ = 0, slices_ = 0, left_ = 0;
+  uint64_t gen_ = 0;
+  bool stop_ = false;
+};
+
 struct DeviceCtx {
   int dev = 0;
   int index = 0;  // position in capy_ctx::devs
@@ -102,6 +139,9 @@ struct DeviceCtx {
   // different devices of a ctx do not serialise
   std::unique_ptr<std::mutex> mu{new std::mutex()};
   std::unique_ptr<DeviceWorker> worker;  // only in a multi-device ctx
+  // staging of pageable host buffers, one double buffer per scratch slot that needs it (created at first use)
+  std::vector<StageSlot> stage{(size_t)kNumScratch};
+  std::unique_ptr<CopyPool> copy_pool;
 };
 
 }  // namespace capy
@@ -135,6 +175,13 @@ int cuda_fail(capy_ctx* ctx, cudaError_t e, const char* what);
 
 // returns nullptr on OOM
 void* scratch_get(DeviceCtx& dc, int slot, size_t bytes);
+
+// host <-> device copies of the host entry points (hostbatch.h); `slot` = the scratch slot of the device buffer
+int copy_in(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t st, int slot, void* d_dst, const void* h_src, size_t bytes);
+int copy_out(capy_ctx* ctx, DeviceCtx& dc, cudaStream_t st, int slot, void* h_dst, const void* d_src, size_t bytes);
+// waits for the staged device-to-host copies of this device and hands their bytes to the caller's buffers
+int stage_drain(capy_ctx* ctx, DeviceCtx& dc);
+void stage_free(DeviceCtx& dc);
 
 // the host arrays registered in dc.host_offs belong to the caller of ONE host entry point: forget them when it returns
 struct HostOffScope {

@@ -1103,7 +1103,10 @@ int capy_sha3_batch(capy_ctx* ctx, int d_bits, const uint8_t* data, const uint64
         uint64_t at = 0, j = 0;
         for (const Run& r : sh.runs) {  // one copy per run of consecutive messages
           const uint64_t b0 = off[r.i0], b1 = off[r.i1];
-          if (b1 > b0) CAPY_CUDA(ctx, cudaMemcpyAsync(d_data + at, data + b0, (size_t)(b1 - b0), cudaMemcpyHostToDevice, st));
+          if (b1 > b0) {
+            const int rc = copy_in(ctx, dc, st, 0, d_data + at, data + b0, (size_t)(b1 - b0));
+            if (rc) return rc;
+          }
           for (uint64_t i = r.i0; i < r.i1; i++) loc[j++] = at + (off[i] - b0);
           at += b1 - b0;
         }
@@ -1114,7 +1117,8 @@ int capy_sha3_batch(capy_ctx* ctx, int d_bits, const uint8_t* data, const uint64
         if (rc) return rc;
         j = 0;
         for (const Run& r : sh.runs) {  // the digests of a run are consecutive on both sides
-          CAPY_CUDA(ctx, cudaMemcpyAsync(digests + r.i0 * ob, d_out + j * ob, (size_t)(r.i1 - r.i0) * ob, cudaMemcpyDeviceToHost, st));
+          rc = copy_out(ctx, dc, st, 2, digests + r.i0 * ob, d_out + j * ob, (size_t)(r.i1 - r.i0) * ob);
+          if (rc) return rc;
           j += r.i1 - r.i0;
         }
         CAPY_CUDA(ctx, cudaStreamSynchronize(st));  // (`loc` stays alive until here)
@@ -1138,7 +1142,8 @@ int capy_sha3_batch(capy_ctx* ctx, int d_bits, const uint8_t* data, const uint64
       if (!d_out) return CAPY_ERR_OOM;
       rc = launch_sha3(ctx, dc, st, d_bits, sp.d_base, sp.d_off, 0, 0, ch.i1 - ch.i0, d_out, flags);
       if (rc) return rc;
-      CAPY_CUDA(ctx, cudaMemcpyAsync(digests + ch.i0 * ob, d_out, (size_t)(ch.i1 - ch.i0) * ob, cudaMemcpyDeviceToHost, st));
+      rc = copy_out(ctx, dc, st, 3 * s + 2, digests + ch.i0 * ob, d_out, (size_t)(ch.i1 - ch.i0) * ob);
+      if (rc) return rc;
     }
     for (int s = 0; s < kNumStreams; s++) CAPY_CUDA(ctx, cudaStreamSynchronize(dc.streams[s]));
     return CAPY_OK;
@@ -1166,10 +1171,12 @@ int capy_sha3_batch_fixed(capy_ctx* ctx, int d_bits, const uint8_t* data, uint64
       uint8_t* d_in = (uint8_t*)scratch_get(dc, 3 * s, in_bytes + 16);
       uint8_t* d_out = (uint8_t*)scratch_get(dc, 3 * s + 2, (size_t)cnt * ob);
       if (!d_in || !d_out) return CAPY_ERR_OOM;
-      CAPY_CUDA(ctx, cudaMemcpyAsync(d_in, data + ch.i0 * stride, in_bytes, cudaMemcpyHostToDevice, st));
-      int rc = launch_sha3(ctx, dc, st, d_bits, d_in, nullptr, msg_len, stride, cnt, d_out);
+      int rc = copy_in(ctx, dc, st, 3 * s, d_in, data + ch.i0 * stride, in_bytes);
       if (rc) return rc;
-      CAPY_CUDA(ctx, cudaMemcpyAsync(digests + ch.i0 * ob, d_out, (size_t)cnt * ob, cudaMemcpyDeviceToHost, st));
+      rc = launch_sha3(ctx, dc, st, d_bits, d_in, nullptr, msg_len, stride, cnt, d_out);
+      if (rc) return rc;
+      rc = copy_out(ctx, dc, st, 3 * s + 2, digests + ch.i0 * ob, d_out, (size_t)cnt * ob);
+      if (rc) return rc;
     }
     for (int s = 0; s < kNumStreams; s++) CAPY_CUDA(ctx, cudaStreamSynchronize(dc.streams[s]));
     return CAPY_OK;
@@ -1215,7 +1222,8 @@ int capy_cshake_batch(capy_ctx* ctx, int d_bits, const uint8_t* data, const uint
       rc = launch_cshake(ctx, dc, st, d_bits, sp.d_base, sp.d_off, ch.i1 - ch.i0, fn_name, fn_len, custom, custom_len,
                          out_bits, d_out);
       if (rc) return rc;
-      CAPY_CUDA(ctx, cudaMemcpyAsync(out + ch.i0 * ob, d_out, (size_t)(ch.i1 - ch.i0) * ob, cudaMemcpyDeviceToHost, st));
+      rc = copy_out(ctx, dc, st, 3 * s + 2, out + ch.i0 * ob, d_out, (size_t)(ch.i1 - ch.i0) * ob);
+      if (rc) return rc;
     }
     for (int s = 0; s < kNumStreams; s++) CAPY_CUDA(ctx, cudaStreamSynchronize(dc.streams[s]));
     return CAPY_OK;
@@ -1325,7 +1333,10 @@ int capy_kmac_xof_batch(capy_ctx* ctx, int d_bits, const uint8_t* keys, const ui
       a.out = d_out_base;
       rc = launch_kmac_xof(ctx, dc, st, a);
       if (rc) return rc;
-      if (ob1 > ob0) CAPY_CUDA(ctx, cudaMemcpyAsync(out + ob0, d_out, (size_t)(ob1 - ob0), cudaMemcpyDeviceToHost, st));
+      if (ob1 > ob0) {
+        rc = copy_out(ctx, dc, st, 6 * s + 4, out + ob0, d_out, (size_t)(ob1 - ob0));
+        if (rc) return rc;
+      }
     }
     for (int s = 0; s < kNumStreams; s++) CAPY_CUDA(ctx, cudaStreamSynchronize(dc.streams[s]));
     return CAPY_OK;
