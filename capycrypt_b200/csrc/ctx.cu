@@ -343,6 +343,8 @@ int capy_gpu_scrub(capy_ctx* ctx) {
     for (Scratch& sc : dc.scratch)
       if (sc.p) CAPY_CUDA(ctx, cudaMemset(sc.p, 0, sc.cap));
     CAPY_CUDA(ctx, cudaDeviceSynchronize());
+    for (StageSlot& ss : dc.stage)  // the page-locked staging halves saw passwords and plaintexts too
+      if (ss.p) memset(ss.p, 0, 2 * kStagePiece);
   }
   return CAPY_OK;
 }

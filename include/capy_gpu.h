@@ -13,7 +13,9 @@
  *  - plain pointers and sizes only; every call returns an int status (CAPY_OK == 0, errors < 0);
  *    nothing throws or aborts across the boundary.
  *  - the caller owns every buffer.  Host entry points are blocking; host pointers may be
- *    pageable (pinned memory from capy_host_alloc is faster).  `_dev` twins take DEVICE
+ *    pageable: large pageable buffers are staged through page-locked buffers of the ctx by a few
+ *    copy threads (env CAPY_COPY_THREADS, default up to 8) -- about 20 GB/s; memory from
+ *    capy_host_alloc goes straight to the DMA engines -- about 47 GB/s.  `_dev` twins take DEVICE
  *    pointers plus a CUDA stream and are asynchronous on that stream.
  *  - batches: `data` is a packed byte array and `off` has n+1 uint64 offsets into it (item i
  *    = data[off[i] .. off[i+1]) ).  `_fixed` variants take one length and a stride instead.
@@ -68,9 +70,10 @@ typedef struct capy_ctx capy_ctx;
 int capy_gpu_init(const int* devices, int n_devices, capy_ctx** out_ctx);
 void capy_gpu_destroy(capy_ctx* ctx);
 int capy_gpu_device_count(const capy_ctx* ctx);
-/* Overwrites every device scratch buffer of the ctx with zeros.  The pipelines keep intermediate secrets there
- * (derived scalars, KMAC key material, staged passwords) until the next call reuses the buffer; the reference does
- * not zeroize either, so this is an extra for callers who want it.  Blocking. */
+/* Overwrites every device scratch buffer of the ctx -- and the page-locked host buffers pageable inputs were staged
+ * through -- with zeros.  The pipelines keep intermediate secrets there (derived scalars, KMAC key material, staged
+ * passwords) until the next call reuses the buffer; the reference does not zeroize either, so this is an extra for
+ * callers who want it.  Blocking. */
 int capy_gpu_scrub(capy_ctx* ctx);
 const char* capy_strerror(int status);
 /* last CUDA error text seen by this ctx (for CAPY_ERR_CUDA) */
