@@ -151,6 +151,89 @@ __global__ void __launch_bounds__(128) chain_warp25_smem(uint64_t* st, int nperm
   if (l < 25) st[(size_t)item * 25 + l] = ((uint64_t)hi << 32) | lo;
 }
 
+// One SHEET (column x: lanes A[x][0..4]) per thread, five threads per state, six states per warp (lanes 30, 31 idle).
+// theta: the column parity is local, D needs the parities of the two neighbour columns (4 SHFL); rho: five local
+// rotations by per-thread amounts; pi: B[y][2x+3y] = A[x][y] is a 5 x 5 transposition between the five threads (10 SHFL,
+// the source thread picks the row its reader wants after a barrel rotation of its five lanes by x); chi: every row needs
+// the lanes of columns x+1 and x+2 (20 SHFL).  34 SHFL + ~80 ALU instructions per round and warp for six states.
+__global__ void __launch_bounds__(128) chain_sheet5(uint64_t* st, int nperm, int n_items) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int l = threadIdx.x & 31;
+  const int g = l / 5 < 6 ? l / 5 : 5, x = l < 30 ? l % 5 : 0;
+  const bool live = l < 30;
+  const int item0 = (t >> 5) * 6 + g;
+  const int item = item0 < n_items ? item0 : 0;
+  const int base = 5 * g;
+  Lane a[5];
+#pragma unroll
+  for (int y = 0; y < 5; y++) {
+    const uint64_t v = st[(size_t)item * 25 + x + 5 * y];
+    a[y].lo = (uint32_t)v;
+    a[y].hi = (uint32_t)(v >> 32);
+  }
+  uint32_t rs[5], rm[5];  // rho: rotation by 32 * rs + rm for the lane of row y
+#pragma unroll
+  for (int y = 0; y < 5; y++) {
+    const uint32_t r = RHO25[x + 5 * y];
+    rs[y] = r >= 32;
+    rm[y] = r & 31;
+  }
+  const int src_m = base + (x + 4) % 5, src_p = base + (x + 1) % 5, src_p2 = base + (x + 2) % 5;
+  int pi_src[5];
+#pragma unroll
+  for (int Y = 0; Y < 5; Y++) pi_src[Y] = base + (3 * Y + x) % 5;
+  const bool b0 = x & 1, b1 = x & 2, b2 = x & 4;
+  const uint32_t is0 = (live && x == 0) ? 0xffffffffu : 0u;
+  const unsigned FULL = 0xffffffffu;
+  for (int p = 0; p < nperm; p++) {
+#pragma unroll 1
+    for (int r = 0; r < 24; r++) {
+      const uint32_t clo = lop_xor3(lop_xor3(a[0].lo, a[1].lo, a[2].lo), a[3].lo, a[4].lo);
+      const uint32_t chi = lop_xor3(lop_xor3(a[0].hi, a[1].hi, a[2].hi), a[3].hi, a[4].hi);
+      const uint32_t mlo = __shfl_sync(FULL, clo, src_m), mhi = __shfl_sync(FULL, chi, src_m);
+      const uint32_t plo = __shfl_sync(FULL, clo, src_p), phi = __shfl_sync(FULL, chi, src_p);
+      const uint32_t r1lo = __funnelshift_l(phi, plo, 1), r1hi = __funnelshift_l(plo, phi, 1);
+      Lane e[5];
+#pragma unroll
+      for (int y = 0; y < 5; y++) {
+        const uint32_t tlo = lop_xor3(a[y].lo, mlo, r1lo), thi = lop_xor3(a[y].hi, mhi, r1hi);
+        const uint32_t ulo = rs[y] ? thi : tlo, uhi = rs[y] ? tlo : thi;
+        e[y].lo = __funnelshift_l(uhi, ulo, rm[y]);
+        e[y].hi = __funnelshift_l(ulo, uhi, rm[y]);
+      }
+      // f[j] = e[(j + x) % 5]: barrel rotation of the five lanes by x (1, 2, 4)
+      Lane f[5];
+#pragma unroll
+      for (int j = 0; j < 5; j++) f[j] = b0 ? e[(j + 1) % 5] : e[j];
+#pragma unroll
+      for (int j = 0; j < 5; j++) e[j] = b1 ? f[(j + 2) % 5] : f[j];
+#pragma unroll
+      for (int j = 0; j < 5; j++) f[j] = b2 ? e[(j + 4) % 5] : e[j];
+      // pi: row Y of the new column comes from thread (3Y + x) % 5, which offers its lane of row (s + 2Y) % 5 = f[2Y % 5]
+      Lane b[5];
+#pragma unroll
+      for (int Y = 0; Y < 5; Y++) {
+        b[Y].lo = __shfl_sync(FULL, f[(2 * Y) % 5].lo, pi_src[Y]);
+        b[Y].hi = __shfl_sync(FULL, f[(2 * Y) % 5].hi, pi_src[Y]);
+      }
+      const uint2 rc = KECCAK_RC[r];
+#pragma unroll
+      for (int Y = 0; Y < 5; Y++) {
+        const uint32_t n1l = __shfl_sync(FULL, b[Y].lo, src_p), n1h = __shfl_sync(FULL, b[Y].hi, src_p);
+        const uint32_t n2l = __shfl_sync(FULL, b[Y].lo, src_p2), n2h = __shfl_sync(FULL, b[Y].hi, src_p2);
+        a[Y].lo = lop_chi(b[Y].lo, n1l, n2l);
+        a[Y].hi = lop_chi(b[Y].hi, n1h, n2h);
+      }
+      a[0].lo ^= rc.x & is0;
+      a[0].hi ^= rc.y & is0;
+    }
+  }
+  if (live && item0 < n_items) {
+#pragma unroll
+    for (int y = 0; y < 5; y++) st[(size_t)item * 25 + x + 5 * y] = ((uint64_t)a[y].hi << 32) | a[y].lo;
+  }
+}
+
 // the same permutation through the WarpKeccak struct the sponge uses, with an early exit in front (what the
 // tiered kernel has) and one XOR per permutation standing in for the absorb
 __global__ void __launch_bounds__(128) chain_warp25_struct(uint64_t* st, int nperm, int n_items, const uint32_t* __restrict__ feed) {
@@ -206,6 +289,24 @@ int main(int argc, char** argv) {
       printf("{\"warps_per_scheduler\": %d, \"warp25_us_per_perm\": %.4f, \"chain_speedup_vs_single\": %.3f, \"warp25_Gperm_s\": %.4f, \"mismatching_lanes\": %zu}\n",
              wps, ms3 * 1e3 / nperm, ms1 / ms3, threads / 32 / (ms3 * 1e-3 / nperm) / 1e9, bad3);
       cudaFree(d3);
+    }
+    {
+      // sheet-per-thread: six states per warp
+      const int n_items8 = threads / 32 * 6;
+      uint64_t* d8; cudaMalloc(&d8, init.size() * 8);
+      cudaMemcpy(d8, init.data(), init.size() * 8, cudaMemcpyHostToDevice);
+      chain_sheet5<<<blocks, 128>>>(d8, 2, n_items8);
+      float ms8;
+      cudaEventRecord(e0); chain_sheet5<<<blocks, 128>>>(d8, nperm, n_items8); cudaEventRecord(e1); cudaEventSynchronize(e1);
+      cudaEventElapsedTime(&ms8, e0, e1);
+      std::vector<uint64_t> r8((size_t)threads * 25), r1d((size_t)threads * 25);
+      cudaMemcpy(r8.data(), d8, r8.size() * 8, cudaMemcpyDeviceToHost);
+      cudaMemcpy(r1d.data(), d1, r1d.size() * 8, cudaMemcpyDeviceToHost);
+      size_t bad8 = 0;
+      for (size_t i = 0; i < (size_t)n_items8 * 25; i++) bad8 += r1d[i] != r8[i];
+      printf("{\"warps_per_scheduler\": %d, \"sheet5_six_states_per_warp_us_per_perm\": %.4f, \"states_per_sm\": %d, \"Gperm_s\": %.4f, \"mismatching_lanes\": %zu}\n",
+             wps, ms8 * 1e3 / nperm, 24 * wps, n_items8 / (ms8 * 1e-3 / nperm) / 1e9, bad8);
+      cudaFree(d8);
     }
     {
       uint64_t* d7; cudaMalloc(&d7, init.size() * 8);
