@@ -37,7 +37,7 @@ MAC_VAR = 7.12e5
 # 448 x (4 S + 3 M) + 112 M + 113 x 9 M + table (1 dbl + 6 add), M = 193, S = 110
 MAC_EXEC_FIXED = 1.23e5
 MAC_EXEC_VAR = 6.86e5
-WARP_TIER_US_PER_PERM = 2.19  # chain speed of the fastest tier (one warp per message), profiles/README.md
+WARP_TIER_US_PER_PERM = 2.04  # chain speed of the fastest tier (one warp per message), profiles/README.md
 PEAK_FALLBACK = {"lop3": 18.52e12, "imad_wide": 8.67e12}  # profiles/r01_peaks_int_pipes.json
 
 
@@ -737,7 +737,7 @@ def extras(eng, dev, peaks, world, dist, rank):
         "longest_chain_perms": longest, "chain_floor_ms": chain_floor_ms, "work_floor_ms": work_floor_ms,
         "frac_of_floor": floor_ms / ms, "ms_one_thread_per_message": ms_solo, "oracle_sample": int(len(pick)),
         "note": "a sponge is sequential per message: the step cannot be shorter than the longest message's chain at the "
-                "fastest tier (1 MiB = 14 564 permutations x 2.19 us with a whole warp per message = chain_floor_ms) nor than "
+                "fastest tier (1 MiB = 14 564 permutations x 2.04 us with a whole warp per message = chain_floor_ms) nor than "
                 "the rank's permutations at the ALU peak (work_floor_ms); frac_of_floor = max of the two / measured"}
     del d5, o5, t_off5
 

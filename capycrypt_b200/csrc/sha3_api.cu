@@ -251,14 +251,14 @@ __global__ void len_scatter_kernel(const uint64_t* __restrict__ off, uint64_t n,
 }
 
 // Measured on B200, per permutation of ONE chain inside the sponge (tools/bench_tier_probe.py, 1 MiB SHA3-512 messages,
-// profiles/README.md): one thread per state 4.6 us; a thread pair 3.55 us; a whole warp per state 2.19 us on an otherwise
-// idle GPU and 2.34 us with every SM busy.  A warp-tier chain issues only ~32 instructions per ~180-clock round, so several
-// can share a scheduler -- but the 18 shuffles of its round go through one shuffle unit per SM (one warp-wide shuffle per
-// clock): with c chains per scheduler a round cannot be shorter than 72 c clocks.  Measured: 2.34 / 2.60 / 3.14 us per
-// permutation at c = 1 / 2 / 3.
-constexpr double kPairChainRatio = 3.55 / 4.6;
+// profiles/README.md round 2): one thread per state 4.6 us; a thread pair 3.08 us; a whole warp per state 2.04 us on an
+// otherwise idle GPU and 2.06 us with every SM busy.  A warp-tier chain issues only ~32 instructions per ~170-clock round,
+// so several can share a scheduler -- but the 18 shuffles of its round go through one shuffle unit per SM (one warp-wide
+// shuffle per clock): with c chains per scheduler a round cannot be shorter than 72 c clocks.  Measured: 2.06 / 2.36 /
+// 3.0 us per permutation at c = 1 / 2 / 3.
+constexpr double kPairChainRatio = 3.08 / 4.6;
 constexpr int kMaxWarpCosched = 3;
-constexpr double kWarpChainRatio[kMaxWarpCosched + 1] = {0.0, 2.34 / 4.6, 2.60 / 4.6, 3.14 / 4.6};
+constexpr double kWarpChainRatio[kMaxWarpCosched + 1] = {0.0, 2.06 / 4.6, 2.36 / 4.6, 3.00 / 4.6};
 
 // Tiers of a chain-bound batch.  cum[k] = number of items in length bins > k (bin = whole blocks of the message).
 // Times are in units of one thread-per-state permutation; an SM hosts ONE block: 4 c warp-tier items (c = 1, 2 or 3

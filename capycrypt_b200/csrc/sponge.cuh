@@ -304,7 +304,7 @@ __device__ __forceinline__ void sponge_item(const SpongeJob& J, uint64_t i, uint
     for (uint64_t b = fb0; b < fb1; b++) {
       q += LANES;
       uint2 nxt[LANES];
-      if (b + 1 < fb1) {
+      if (b + 1 < fb1) {  // (as predicated loads, the way the pair tier has them, this loop measured 1 % slower)
 #pragma unroll
         for (int j = 0; j < LANES; j++) nxt[j] = ld_lane<COH>(q + j);
       }
@@ -630,15 +630,12 @@ __device__ __noinline__ void sponge_item_warp(const SpongeJob& J, uint64_t i) { 
 #pragma unroll 1
   for (uint64_t b = skip; b < nblocks; b++) {
     uint32_t vlo, vhi;
+    bool pf = false;
     if (b >= fb0 && b < fb1) {  // warp-uniform: one item per warp
       vlo = __funnelshift_r(w0, w1, sh);
       vhi = __funnelshift_r(w1, w2, sh);
       q += 2 * LANES;
-      if (b + 1 < fb1) {
-        w0 = __ldg(q);
-        w1 = __ldg(q + 1);
-        w2 = sh != 0 ? __ldg(q + 2) : 0u;
-      }
+      pf = b + 1 < fb1;
     } else {
       const uint64_t v = sponge_lane_ool(&g, b * STRIDE + 8ull * (mine ? l : 0));
       vlo = (uint32_t)v;
@@ -646,6 +643,10 @@ __device__ __noinline__ void sponge_item_warp(const SpongeJob& J, uint64_t i) { 
     }
     lo ^= vlo & keep;
     hi ^= vhi & keep;
+    // next block: predicated loads behind the point where the two paths meet (see sponge_item_pair)
+    if (pf) w0 = __ldg(q);
+    if (pf) w1 = __ldg(q + 1);
+    if (pf && sh != 0) w2 = __ldg(q + 2);
     wk.permute(lo, hi);
   }
   // squeeze (sponge.rs:25-34, minus the dropped final permutation)
