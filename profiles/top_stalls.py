@@ -29,3 +29,14 @@ print("== top by long scoreboard")
 for d in sorted(data, key=lambda d: -d[0])[:18]: print(f"{d[0]:9.0f} {d[1]:9.0f} {d[2]:9.0f}  {d[3]}")
 print("== top by all samples")
 for d in sorted(data, key=lambda d: -d[2])[:18]: print(f"{d[0]:9.0f} {d[1]:9.0f} {d[2]:9.0f}  {d[3]}")
+
+import re
+agg = collections.Counter()
+for d in data:
+    t = re.sub(r"^@!?U?P\d+\s+", "", d[3].strip())
+    op = t.split()[0] if t else "?"
+    base = op.split(".")[0]
+    if base == "IMAD" and ".WIDE" in op: base = "IMAD.WIDE"
+    agg[base] += d[2]
+print("== samples by opcode")
+for k, v in agg.most_common(14): print(f"{v:10.0f} {100 * v / S:5.1f} %  {k}")
