@@ -156,3 +156,34 @@ def test_cfg5_mixed_sha3_512_2gib_all_tiers(engine, oracle):
     engine.sha3_dev(t_data, t_off, 512, t_out)
     torch.cuda.synchronize()
     assert np.array_equal(t_out.cpu().numpy().reshape(n, 64), got)
+
+
+def test_offsets_beyond_4gib(engine, oracle):
+    """A device-resident batch of 5 GiB: byte offsets cross 2^32 (the reference indexes with usize; a 32-bit slip in an
+    offset, a pointer difference or a block count would show on the far side of the boundary).  Mixed lengths so that the
+    ragged launch orders and tiers the batch; the sample takes the messages around the 4 GiB mark, the last ones and random
+    ones on both sides.  Matches compute_sha3_hash over many messages (sha3/hashable.rs:19-21)."""
+    import torch
+
+    rnd = np.random.default_rng(55)
+    target = 5 << 30
+    lens = np.exp(rnd.uniform(np.log(64), np.log(256 << 10), size=400_000)).astype(np.int64)
+    lens = lens[: int(np.searchsorted(np.cumsum(lens), target)) + 1]
+    n = len(lens)
+    off = np.zeros(n + 1, dtype=np.int64)
+    off[1:] = np.cumsum(lens)
+    assert off[-1] > (1 << 32) + (1 << 29)
+    data = torch.empty(int(off[-1]) + 16, dtype=torch.uint8, device="cuda")
+    data.random_(0, 256)
+    t_off = torch.from_numpy(off).cuda()
+    out = torch.zeros(n * 64, dtype=torch.uint8, device="cuda")
+    engine.sha3_dev(data, t_off, 512, out)
+    torch.cuda.synchronize()
+    k = int(np.searchsorted(off, 1 << 32))  # first message that starts at or beyond 4 GiB
+    idx = np.unique(np.concatenate([np.arange(k - 8, k + 8), np.arange(n - 8, n), np.arange(8),
+                                    rnd.choice(k, size=64, replace=False), k + rnd.choice(n - k, size=64, replace=False)]))
+    msgs = [data[int(off[i]):int(off[i + 1])].cpu().numpy() for i in idx]
+    s_data, s_off = pack(msgs)
+    want = oracle.sha3_batch(s_data, s_off, 512, threads=0)
+    got = out.view(n, 64)[torch.from_numpy(idx).cuda()].cpu().numpy()
+    assert np.array_equal(got, want)
