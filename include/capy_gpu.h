@@ -119,6 +119,8 @@ int capy_plan_tiers3(const uint32_t* items_longer_than, uint32_t n_bins, uint64_
  * for n items that absorb absorb_blocks blocks (after the cached prefix) and run squeeze_extra permutations between
  * squeeze blocks, 0 when the batch is launched as it is. */
 int capy_chain_cut(int sm_count, uint64_t n, uint64_t absorb_blocks, uint64_t squeeze_extra, uint64_t* cut_after_blocks);
+/* (environment, read at every launch: CAPY_NO_CHAIN_SPLIT=1 launches such batches uncut -- the A/B switch of the probes
+ * and of tests/test_chain_split_gpu.py; results are the same bytes either way) */
 
 /* ---- diagnostics: how a ragged sponge batch is divided over the devices of a ctx (no GPU needed) ------------------- */
 /* owner[i] = index of the device that hashes item i when capy_sha3_batch runs on a ctx of `parts` devices: the outliers
