@@ -447,25 +447,8 @@ __device__ __forceinline__ void sponge_item(const SpongeJob& J, uint64_t i, uint
 // prefetch loads of the hot path: the first instruction of the permutation sits behind the point where all paths of a step
 // meet, and there the compiler waited for "the scoreboard" -- i.e. for the loads of the NEXT block that had just been
 // issued (ncu: 15 % of all stall samples of the pair tier on that one instruction, long scoreboard).  A call returns with
-// nothing in flight.
+// nothing in flight.  (The squeeze-block emit of the pair tier stays inline: out of line it measured 2 % slower.)
 __device__ __noinline__ uint64_t sponge_lane_ool(const SpongeGeom* g, uint64_t o) { return g->lane(o); }
-
-__device__ __noinline__ void pair_emit_ool(uint8_t* o, const uint8_t* xi, uint64_t out_bytes, uint64_t produced, uint32_t sq_lanes,
-                                           uint32_t half, bool o_aligned, const uint32_t* hw /* lanes 0..20, this thread's halves */) {
-#pragma unroll 1
-  for (int j = 0; j < 21; j++) {
-    const uint64_t hp = produced + 8ull * j + 4ull * half;  // this thread's four bytes of lane j
-    if (j < (int)sq_lanes && hp < out_bytes) {
-      if (o_aligned && hp + 4 <= out_bytes) {
-        uint32_t v = hw[j];
-        if (xi) v ^= *reinterpret_cast<const uint32_t*>(xi + hp);
-        *reinterpret_cast<uint32_t*>(o + hp) = v;
-      } else {
-        for (int k = 0; k < 4 && hp + k < out_bytes; k++) o[hp + k] = (uint8_t)(hw[j] >> (8 * k)) ^ (xi ? xi[hp + k] : (uint8_t)0);
-      }
-    }
-  }
-}
 
 template <int LANES>
 __device__ __forceinline__ void sponge_item_pair(const SpongeJob& J, uint64_t i, bool valid, uint32_t half) {
@@ -519,14 +502,6 @@ __device__ __forceinline__ void sponge_item_pair(const SpongeJob& J, uint64_t i,
     }
   }
 
-#if defined(CAPY_PAIR_OOL_EMIT)
-  auto emit = [&](uint64_t sb) {  // squeeze block sb of this item (sponge.rs:25-34)
-    uint32_t hw[21];
-#pragma unroll
-    for (int j = 0; j < 21; j++) hw[j] = h[j];
-    pair_emit_ool(o, xi, out_bytes, sb * sq_bytes, sq_lanes, half, o_aligned, hw);
-  };
-#else
   auto emit = [&](uint64_t sb) {  // squeeze block sb of this item (sponge.rs:25-34)
     const uint64_t produced = sb * sq_bytes;
 #pragma unroll
@@ -543,7 +518,6 @@ __device__ __forceinline__ void sponge_item_pair(const SpongeJob& J, uint64_t i,
       }
     }
   };
-#endif
 
 #pragma unroll 1
   for (uint64_t s = 0; s <= warp_steps; s++) {
@@ -568,7 +542,6 @@ __device__ __forceinline__ void sponge_item_pair(const SpongeJob& J, uint64_t i,
     } else if (s <= n_steps && out_bytes) {
       emit(s - n_absorb);
     }
-#if !defined(CAPY_PAIR_PF_IN_BRANCH)
     // The loads of the next block are issued HERE, as predicated loads on the straight line into the permutation.  Inside
     // the absorb branch they sat in front of the point where the paths of a step meet, and the first instruction of the
     // permutation waited there for the scoreboard they share with the rare paths -- i.e. for the loads just issued
@@ -579,15 +552,6 @@ __device__ __forceinline__ void sponge_item_pair(const SpongeJob& J, uint64_t i,
       if (pf) c0[j] = __ldg(q + 2 * j);
       if (pf1) c1[j] = __ldg(q + 2 * j + 1);
     }
-#else
-    if (pf) {
-#pragma unroll
-      for (int j = 0; j < LANES; j++) {
-        c0[j] = __ldg(q + 2 * j);
-        c1[j] = sh != 0 ? __ldg(q + 2 * j + 1) : 0u;
-      }
-    }
-#endif
     if (s < warp_steps) keccak_f1600_pair(h, half);
   }
 }
