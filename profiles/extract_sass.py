@@ -4,6 +4,8 @@ usage: python profiles/extract_sass.py
   keccak_pair_round.sass   one iteration (4 rounds) of the split-lane permutation inside sponge_tiered_kernel<9>
   keccak_warp_round.sass   the first rounds of the unrolled one-lane-per-thread permutation
   fe_mul.sass / fe_sqr.sass the out-of-line field multiplication / squaring of ed448_var.cu
+  pair_prefetch_before_permutation.sass   the pair tier's step: predicated loads of the next block, then the permutation
+  chain_ticket_and_wait.sass / chain_report.sass   sponge_chain_kernel<17>: ticket, dependency wait, completion report
   opcode_histograms.txt    instruction mix per kernel
 """
 import collections
@@ -77,6 +79,26 @@ dump(os.path.join(OUT, "keccak_pair_round.sass"), "sponge_tiered_kernel<9>, pair
 idx = [i for i, (_, t) in enumerate(tier) if "SHFL.IDX PT" in t]
 dump(os.path.join(OUT, "keccak_warp_round.sass"), "sponge_tiered_kernel<9>, warp tier: first two rounds of the unrolled one-lane-per-thread permutation",
      tier[idx[0] - 6: idx[36] + 12])
+
+# the step of the pair tier in front of the permutation: the loads of the next block as predicated LDGs on the straight
+# line into the first round (round 2: they used to sit inside the absorb branch, and the first XOR of the permutation
+# waited for them)
+first_bfly = bfly[0]
+ldg = [i for i, (_, t) in enumerate(tier) if "LDG.E.CONSTANT" in t and i < first_bfly]
+dump(os.path.join(OUT, "pair_prefetch_before_permutation.sass"),
+     "sponge_tiered_kernel<9>, pair tier: predicated loads of the next block, then the first instructions of the permutation",
+     tier[max(0, ldg[-1] - 24): first_bfly + 4])
+
+chain = next(v for k, v in sha3.items() if "sponge_chain_kernelILi17E" in k)
+ns = [i for i, (_, t) in enumerate(chain) if "NANOSLEEP" in t]
+at = [i for i, (_, t) in enumerate(chain) if t.split()[0].startswith(("ATOM", "RED")) or " ATOM" in t or " RED" in t]
+if ns:
+    dump(os.path.join(OUT, "chain_ticket_and_wait.sass"),
+         "sponge_chain_kernel<17>: ticket (ATOM), job / block from the ticket, job 1 waiting for the job-0 block of its items",
+         chain[max(0, at[0] - 6): ns[-1] + 10])
+if len(at) > 1:
+    dump(os.path.join(OUT, "chain_report.sass"), "sponge_chain_kernel<17>: a job-0 warp reports (fence, RED) after storing its states",
+         chain[max(0, at[-1] - 40): at[-1] + 3])
 
 vb = next(v for k, v in var.items() if "var_base_kernel" in k)
 calls = collections.Counter(re.search(r"0x([0-9a-f]+)", t).group(1) for _, t in vb if t.startswith("CALL"))
