@@ -1365,7 +1365,19 @@ int capy_fips_shake_batch_dev(capy_ctx* ctx, int dev_index, void* stream, int sh
   J.out = d_out;
   J.out_stride = J.out_bytes = out_bytes;
   J.n = n;
-  return launch_sponge(ctx, ctx->devs[dev_index], (cudaStream_t)stream, (int)J.rate / 8, J);
+  DeviceCtx& dc = ctx->devs[dev_index];
+  LaunchPlan plan;  // longest first, tiers for chain-bound batches, chains of a uniform batch cut in two: as for cSHAKE
+  int rc = plan_ragged(ctx, dc, (cudaStream_t)stream, d_off, n, J.rate, &plan);
+  if (rc) return rc;
+  J.order = plan.order;
+  const int lanes = (int)J.rate / 8;
+  if (!plan.order && plan.uniform_blocks) {
+    const uint64_t sq = 8ull * J.sq_lanes;
+    uint64_t cut;
+    if (chain_cut(dc.sm_count, n, plan.uniform_blocks, (out_bytes + sq - 1) / sq - 1, &cut))
+      return launch_sponge_chain(ctx, dc, (cudaStream_t)stream, lanes, J, cut);
+  }
+  return launch_sponge(ctx, dc, (cudaStream_t)stream, lanes, J, plan);
 }
 
 }  // extern "C"

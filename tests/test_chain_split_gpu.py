@@ -198,3 +198,39 @@ def test_sha3_equal_long_messages(engine, oracle, d, mlen):
     idx = torch.from_numpy(pick).cuda()
     want = oracle.sha3_batch(data.view(N, mlen)[idx].cpu().numpy().reshape(-1), np.arange(65, dtype=np.uint64) * mlen, d, threads=0)
     assert np.array_equal(f_cut.view(N, d // 8)[idx].cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("bits,mlen,out_bytes", [(256, 3000, 64), (128, 3000, 500), (256, 2000, 2000)])
+def test_fips_shake_cut_and_ragged(engine, bits, mlen, out_bytes):
+    """FIPS 202 SHAKE128 / SHAKE256 (no reference counterpart; checked against hashlib): a uniform batch that is cut, and a
+    ragged one that is ordered longest first"""
+    import hashlib
+
+    g = torch.Generator(device="cuda")
+    g.manual_seed(bits + mlen)
+    data = torch.randint(0, 256, (N * mlen,), dtype=torch.uint8, device="cuda", generator=g)
+    off = torch.arange(N + 1, dtype=torch.int64, device="cuda") * mlen
+
+    def run():
+        out = torch.zeros(N * out_bytes, dtype=torch.uint8, device="cuda")
+        engine.fips_shake_dev(data, off, bits, out_bytes, out)
+        torch.cuda.synchronize()
+        return out
+
+    cut, plain = _both(run)
+    assert torch.equal(cut, plain)
+    h = hashlib.shake_256 if bits == 256 else hashlib.shake_128
+    for i in (0, 1, N // 3, N - 1):
+        m = data[i * mlen:(i + 1) * mlen].cpu().numpy().tobytes()
+        assert cut[i * out_bytes:(i + 1) * out_bytes].cpu().numpy().tobytes() == h(m).digest(out_bytes)
+    # ragged: lengths 0..5000 (sorted launch), same check
+    rnd = np.random.default_rng(bits)
+    lens = rnd.integers(0, 5000, size=3000)
+    o2 = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    d2 = data[: int(o2[-1])]
+    out2 = torch.zeros(3000 * out_bytes, dtype=torch.uint8, device="cuda")
+    engine.fips_shake_dev(d2, torch.from_numpy(o2).cuda(), bits, out_bytes, out2)
+    torch.cuda.synchronize()
+    for i in (0, 7, 1500, 2999):
+        m = d2[int(o2[i]):int(o2[i + 1])].cpu().numpy().tobytes()
+        assert out2[i * out_bytes:(i + 1) * out_bytes].cpu().numpy().tobytes() == h(m).digest(out_bytes)
