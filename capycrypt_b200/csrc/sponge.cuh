@@ -348,17 +348,18 @@ __device__ __forceinline__ void sponge_item(const SpongeJob& J, uint64_t i, uint
     }
   }
 
-  // Plain SHA3-d / FIPS SHAKE (no prefix, no key, one trailer byte, rate = 8 LANES): the stream ends with exactly one
-  // block "message tail | trailer | zeros | 0x80", and short messages ARE that block.  It is assembled from aligned
-  // 32-bit words + funnel shift like the whole-message blocks (only words that hold a message byte are read), the bytes
-  // behind the message masked away: ~200 instructions instead of the ~2 500 of the general lane-by-lane assembly.
-  // 2^20 ragged messages of 1..135 bytes through capy_sha3_batch_dev: 0.52 -> 0.32 ms (profiles/README.md, r02c).
-  const bool simple_tail = !CHAIN && J.prefix_len == 0 && J.keys == nullptr && J.q4_rate == 0 && J.trailer_len == 1 &&
-                           J.rate == (uint32_t)STRIDE && fb1 + 1 == nblocks;
+  // The stream usually ends with exactly one block "message tail | trailer | zeros | 0x80" that starts inside (or at the
+  // end of) the message, and short messages ARE that block.  It is assembled from aligned 32-bit words + funnel shift like
+  // the whole-message blocks (only words that hold a message byte are read), the bytes behind the message masked away:
+  // ~250 instructions instead of the ~2 500 of the general lane-by-lane assembly.  2^20 ragged messages of 1..135 bytes
+  // through capy_sha3_batch_dev: 0.52 -> 0.32 ms (profiles/README.md, r02c).  Not for the Q4 double padding, a rate that
+  // is not a whole number of lanes (Q7 at D224), or a trailer that spills into a second block: those take the general path.
+  const bool simple_tail = !(CHAIN && J.chain_out) && J.q4_rate == 0 && J.rate == (uint32_t)STRIDE && fb1 + 1 == nblocks &&
+                           fb1 * STRIDE >= g.x0 && fb1 * STRIDE <= g.x1 && fb1 >= J.skip_blocks;
   if (simple_tail) {
     const uint64_t s0 = fb1 * STRIDE;
     const uint32_t rem = (uint32_t)(g.x1 - s0);  // message bytes in this block: 0 .. STRIDE - 1
-    const uint8_t* tp = g.x + s0;
+    const uint8_t* tp = g.x + (s0 - g.x0);
     const uint32_t ph = (uint32_t)(reinterpret_cast<uintptr_t>(tp) & 3u), tsh = 8u * ph;
     const uint32_t* tq = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(tp) & ~(uintptr_t)3);
     const uint32_t nw = rem ? (rem + ph + 3u) / 4u : 0u;  // words that hold at least one message byte
@@ -368,21 +369,25 @@ __device__ __forceinline__ void sponge_item(const SpongeJob& J, uint64_t i, uint
       w[j] = 0u;
       if ((uint32_t)j < nw) w[j] = ld_word<COH>(tq + j);
     }
+    const uint64_t tr = g.trailer;  // up to three bytes (KMACXOF: 00 01 04), little-endian
 #pragma unroll
     for (int j = 0; j < LANES; j++) {
       uint32_t lo = __funnelshift_r(w[2 * j], w[2 * j + 1], tsh), hi = __funnelshift_r(w[2 * j + 1], w[2 * j + 2], tsh);
       const uint32_t o = 8u * j;
-      // keep the message bytes below rem, put the trailer byte at rem
+      // keep the message bytes below rem, put the trailer bytes at rem ..
       const uint32_t klo = rem > o ? (rem - o >= 4u ? 0xffffffffu : (1u << (8u * (rem - o))) - 1u) : 0u;
       const uint32_t khi = rem > o + 4u ? (rem - o - 4u >= 4u ? 0xffffffffu : (1u << (8u * (rem - o - 4u))) - 1u) : 0u;
       lo &= klo;
       hi &= khi;
-      if (rem >= o && rem < o + 4u) lo |= g.trailer << (8u * (rem - o));
-      if (rem >= o + 4u && rem < o + 8u) hi |= g.trailer << (8u * (rem - o - 4u));
+      if (rem + 4u > o && rem < o + 8u) {
+        const uint64_t t = rem >= o ? tr << (8u * (rem - o)) : tr >> (8u * (o - rem));
+        lo |= (uint32_t)t;
+        hi |= (uint32_t)(t >> 32);
+      }
       a[j].lo ^= lo;
       a[j].hi ^= hi;
     }
-    if (g.has_pad) a[LANES - 1].hi ^= 0x80000000u;  // (Q1: no 0x80 when the trailer byte filled the block)
+    if (g.has_pad) a[LANES - 1].hi ^= 0x80000000u;  // (Q1: no 0x80 when the trailer filled the block exactly)
     keccak_f1600(a);
   } else {
 #pragma unroll 1
