@@ -118,6 +118,9 @@ struct SpongeGeom {
   bool has_pad1, has_pad;
   uint8_t hdr[12];  // left_encode(w) || left_encode(8 * klen): the head of bytepad(encode_string(K), w)
 
+  // RATE_HINT: the caller's compile-time rate (8 LANES); when the job's rate equals it -- always, except for the 172-byte
+  // rate of cSHAKE at D224 (Q7) -- the two divisions by the rate are divisions by a constant
+  template <uint32_t RATE_HINT = 0>
   __device__ __forceinline__ void init(const SpongeJob& J, uint64_t i) {
     prefix = J.prefix;
     prefix_len = J.prefix_len;
@@ -169,9 +172,16 @@ struct SpongeGeom {
       has_pad1 = rem1 != 0;
       if (has_pad1) p1 = t1 + (J.q4_rate - rem1);
     }
-    const uint64_t rem = p1 % J.rate;
-    padded = rem ? p1 + (J.rate - rem) : p1;  // Q1: no pad block when aligned
-    nblocks = padded / J.rate;
+    uint64_t rem;
+    if (RATE_HINT != 0 && J.rate == RATE_HINT) {
+      rem = p1 % RATE_HINT;
+      padded = rem ? p1 + (RATE_HINT - rem) : p1;  // Q1: no pad block when aligned
+      nblocks = padded / RATE_HINT;
+    } else {
+      rem = p1 % J.rate;
+      padded = rem ? p1 + (J.rate - rem) : p1;
+      nblocks = padded / J.rate;
+    }
     has_pad = rem != 0;
     if (J.fips_pad && !has_pad) trailer |= 0x80u << (8 * (trailer_len - 1));
   }
@@ -231,7 +241,7 @@ struct SpongeGeom {
 template <int LANES, bool CHAIN = false, bool COH = false>
 __device__ __forceinline__ void sponge_item(const SpongeJob& J, uint64_t i, uint64_t rank = 0) {
   SpongeGeom g;
-  g.init(J, i);
+  g.template init<8u * LANES>(J, i);
   Lane a[25];
   if (CHAIN && J.chain_in) {
 #pragma unroll
